@@ -1,0 +1,106 @@
+"""ctypes binding of libgpuar_b200.so (the C ABI in include/gpuar_b200.h).
+
+The library is the product: if it is missing or cannot run on this device, every
+call raises -- there is no Python, PyTorch or CPU fallback for the codec.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgpuar_b200.so")
+
+PACKET = 8192          # GPUAR_PACKET_BYTES  (reference gpu.h:13)
+SLOT = 8704            # GPUAR_SLOT_BYTES    (reference gpu.h:12)
+FILE_HEADER = 20       # GPUAR_FILE_HEADER   (reference file_header.hpp:19-22)
+PAD = 64               # GPUAR_PAD_BYTES
+
+E_ARG, E_FORMAT, E_NODEVICE, E_UNSUPPORTED = -1, -2, -3, -4
+
+
+class GpuarError(RuntimeError):
+    def __init__(self, code: int, what: str):
+        self.code = code
+        super().__init__(f"{what}: {strerror(code)} ({code})")
+
+
+_u8p = C.POINTER(C.c_uint8)
+_vp = C.c_void_p
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); kept in the order of include/gpuar_b200.h
+SIGNATURES = {
+    "gpuar_b200_abi_version": (C.c_int, []),
+    "gpuar_b200_strerror": (C.c_char_p, [C.c_int]),
+    "gpuar_b200_init": (C.c_int, []),
+    "gpuar_b200_packets": (_sz, [_sz]),
+    "gpuar_b200_payload_bound": (_sz, [_sz]),
+    "gpuar_b200_encode_scratch_bytes": (_sz, [_sz]),
+    "gpuar_b200_index_scratch_bytes": (_sz, [_sz]),
+    "gpuar_b200_encode": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
+    "gpuar_b200_index": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _vp, _sz, _vp]),
+    "gpuar_b200_decode": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _sz, _vp]),
+    "gpuar_b200_compress_host": (C.c_int, [_vp, _sz, _vp, _sz, C.POINTER(_sz)]),
+    "gpuar_b200_decompress_host": (C.c_int, [_vp, _sz, _vp, _sz, C.POINTER(_sz)]),
+    "gpuar_b200_gip_raw_size": (C.c_int, [_vp, _sz, C.POINTER(C.c_uint64)]),
+    "gpuar_b200_write_header": (None, [_vp, C.c_uint64, C.c_uint64]),
+    "gpuar_b200_check_header": (C.c_int, [_vp]),
+    "gpuar_b200_peer_concat": (C.c_int, [_vp, C.c_int, _sz, _vp, C.c_int, _sz, _vp]),
+    "gpuar_b200_ipc_export": (C.c_int, [_vp, _vp]),
+    "gpuar_b200_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "gpuar_b200_ipc_close": (C.c_int, [_vp]),
+    "initConstantRange": (None, []),
+    "garCompressExecutor": (None, [_vp, _sz, _vp, C.c_uint32]),
+    "garDecompressExecutor": (None, [_vp, _sz, _vp, C.c_uint32]),
+    "gpuar_b200_profile": (None, [C.c_int]),
+    "gpuar_b200_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "gpuar_b200_launch_count": (C.c_uint64, []),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the library (once).  Raises if it has not been built -- see __graft_entry__.build()."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `make -C gpuar_b200/csrc` "
+                "(or `python -c 'import __graft_entry__ as g; g.build()'`); there is no fallback path")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def strerror(code: int) -> str:
+    return lib().gpuar_b200_strerror(int(code)).decode()
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise GpuarError(code, what)
+
+
+SPANS = ("encode", "compact", "index", "decode")
+
+
+def profile(enable: bool) -> None:
+    lib().gpuar_b200_profile(1 if enable else 0)
+
+
+def profile_read() -> dict:
+    """{"encode": (ms, spans), ...} accumulated since the last read (synchronises the spans)."""
+    ms = (C.c_double * 4)()
+    calls = (C.c_uint64 * 4)()
+    check(lib().gpuar_b200_profile_read(ms, calls), "gpuar_b200_profile_read")
+    return {name: (float(ms[k]), int(calls[k])) for k, name in enumerate(SPANS)}
+
+
+def launch_count() -> int:
+    return int(lib().gpuar_b200_launch_count())

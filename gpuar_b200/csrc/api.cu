@@ -1,0 +1,419 @@
+// api.cu -- the C ABI of libgpuar_b200.so (include/gpuar_b200.h): argument checking,
+// scratch layout, the host-buffer pipelines and the reference-named shims.
+#include "../../include/gpuar_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace gpuar {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline size_t packets_of(size_t n) { return (n + kPacket - 1) / kPacket; }
+
+// encode scratch: [slots: packets*8704 + 64][sizes: packets*4][descriptors][pad]
+struct EncodePlan {
+    size_t packets, off_slots, off_sizes, off_desc, total;
+};
+static EncodePlan encode_plan(size_t n)
+{
+    EncodePlan p{};
+    p.packets = packets_of(n);
+    size_t o = 0;
+    p.off_slots = o;
+    o += align_up(p.packets * (size_t)kSlot + 64, 256);
+    p.off_sizes = o;
+    o += align_up(p.packets * 4 + 4, 256);
+    p.off_desc = o;
+    o += align_up(compact_desc_bytes(p.packets), 256);
+    p.total = o;
+    return p;
+}
+
+static int ck(cudaError_t e) { return (int)e; }
+
+// ---- optional per-kernel timing (bench.py's roofline): CUDA events recorded on the
+// caller's stream around each kernel of an entry point; off by default
+struct Span { cudaEvent_t a, b; int what; };
+static bool g_profile = false;
+static std::vector<Span> g_spans;
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t take_event()
+{
+    cudaEvent_t e = nullptr;
+    if (!g_event_pool.empty()) { e = g_event_pool.back(); g_event_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+struct Scope {                                   // one timed span on stream st
+    Span s{};
+    cudaStream_t st;
+    bool on;
+    Scope(int what, cudaStream_t stream) : st(stream), on(g_profile)
+    {
+        if (!on) return;
+        s.what = what; s.a = take_event(); s.b = take_event();
+        cudaEventRecord(s.a, st);
+    }
+    ~Scope()
+    {
+        if (!on) return;
+        cudaEventRecord(s.b, st);
+        g_spans.push_back(s);
+    }
+};
+
+// ---- per-device cache of staging buffers for the host-buffer entry points
+struct DeviceBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t need(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+};
+constexpr int kLanes = 3;                        // chunks in flight in compress_host
+struct HostPath {
+    int device = -1;
+    cudaStream_t stream[kLanes] = {}, copy = nullptr;
+    cudaEvent_t done[kLanes] = {}, ready = nullptr;
+    DeviceBuf in[kLanes], pay[kLanes], scratch[kLanes];
+    DeviceBuf big_in, big_out, big_scratch, offsets, result;
+    uint64_t *h_total = nullptr;                 // pinned: per-lane payload totals + index result
+};
+static std::mutex g_mu;
+static std::vector<HostPath *> g_paths;
+
+static int host_path(HostPath **out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return GPUAR_E_NODEVICE;
+    for (HostPath *h : g_paths)
+        if (h->device == dev) { *out = h; return 0; }
+    HostPath *h = new HostPath();
+    h->device = dev;
+    for (int i = 0; i < kLanes; ++i) {
+        if ((e = cudaStreamCreateWithFlags(&h->stream[i], cudaStreamNonBlocking)) != cudaSuccess) return ck(e);
+        if ((e = cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming)) != cudaSuccess) return ck(e);
+    }
+    if ((e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking)) != cudaSuccess) return ck(e);
+    if ((e = cudaEventCreateWithFlags(&h->ready, cudaEventDisableTiming)) != cudaSuccess) return ck(e);
+    if ((e = cudaMallocHost(&h->h_total, 16 * sizeof(uint64_t))) != cudaSuccess) return ck(e);
+    g_paths.push_back(h);
+    *out = h;
+    return 0;
+}
+
+}  // namespace gpuar
+
+using namespace gpuar;
+
+extern "C" {
+
+int gpuar_b200_abi_version(void) { return 1; }
+
+const char *gpuar_b200_strerror(int code)
+{
+    switch (code) {
+    case 0: return "ok";
+    case GPUAR_E_ARG: return "bad argument or buffer too small";
+    case GPUAR_E_FORMAT: return "malformed .gip header or packet chain";
+    case GPUAR_E_NODEVICE: return "no usable CUDA device";
+    case GPUAR_E_UNSUPPORTED: return "stream layout not supported by the device path";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int gpuar_b200_init(void)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) return GPUAR_E_NODEVICE;
+    if ((e = cudaFree(nullptr)) != cudaSuccess) return ck(e);
+    // the kernels are built for sm_100a only: fail here, loudly, on anything else
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, probe_kernel());
+    if (e != cudaSuccess) { cudaGetLastError(); return GPUAR_E_NODEVICE; }
+    return 0;
+}
+
+size_t gpuar_b200_packets(size_t n) { return packets_of(n); }
+size_t gpuar_b200_payload_bound(size_t n) { return packets_of(n) * (size_t)kSlot + GPUAR_PAD_BYTES; }
+size_t gpuar_b200_encode_scratch_bytes(size_t n) { return encode_plan(n).total; }
+size_t gpuar_b200_index_scratch_bytes(size_t c) { return index_scratch_bytes(c); }
+uint64_t gpuar_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int gpuar_b200_encode(const uint8_t *d_in, size_t n, uint8_t *d_payload, size_t payload_cap,
+                      uint64_t *d_payload_bytes, uint32_t *d_packet_sizes, void *d_scratch,
+                      size_t scratch_bytes, void *stream)
+{
+    const EncodePlan p = encode_plan(n);
+    if (!d_payload_bytes || (n && (!d_in || !d_payload || !d_scratch))) return GPUAR_E_ARG;
+    if (((uintptr_t)d_in | (uintptr_t)d_payload | (uintptr_t)d_scratch) & 15u) return GPUAR_E_ARG;
+    if (payload_cap < gpuar_b200_payload_bound(n) || scratch_bytes < p.total) return GPUAR_E_ARG;
+    if (p.packets > 0xFFFFFFF0ull) return GPUAR_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *s = static_cast<uint8_t *>(d_scratch);
+    uint32_t *sizes = d_packet_sizes ? d_packet_sizes : reinterpret_cast<uint32_t *>(s + p.off_sizes);
+    cudaError_t e;
+    {
+        Scope t(GPUAR_SPAN_ENCODE, st);
+        e = launch_encode_slots(d_in, n, s + p.off_slots, kSlot, sizes, st);
+    }
+    if (e != cudaSuccess) return ck(e);
+    {
+        Scope t(GPUAR_SPAN_COMPACT, st);
+        e = launch_compact(s + p.off_slots, kSlot, sizes, (uint32_t)p.packets, d_payload,
+                           reinterpret_cast<uint64_t *>(s + p.off_desc), d_payload_bytes, st);
+    }
+    return ck(e);
+}
+
+int gpuar_b200_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets, size_t max_packets,
+                     uint64_t *d_result, void *d_scratch, size_t scratch_bytes, void *stream)
+{
+    if (!d_result || !d_scratch || (c && (!d_payload || !d_offsets))) return GPUAR_E_ARG;
+    if (((uintptr_t)d_payload | (uintptr_t)d_scratch) & 15u) return GPUAR_E_ARG;
+    if (scratch_bytes < index_scratch_bytes(c)) return GPUAR_E_ARG;
+    Scope t(GPUAR_SPAN_INDEX, (cudaStream_t)stream);
+    return ck(launch_index(d_payload, c, d_offsets, max_packets, d_result, d_scratch, scratch_bytes,
+                           (cudaStream_t)stream));
+}
+
+int gpuar_b200_decode(const uint8_t *d_payload, size_t c, const uint64_t *d_offsets, size_t n_packets,
+                      uint8_t *d_out, size_t out_cap, void *stream)
+{
+    if (!n_packets) return 0;
+    if (!d_payload || !d_offsets || !d_out) return GPUAR_E_ARG;
+    if (((uintptr_t)d_payload | (uintptr_t)d_out) & 15u) return GPUAR_E_ARG;
+    if (n_packets > 0xFFFFFFF0ull || out_cap < n_packets * (size_t)kPacket) return GPUAR_E_ARG;
+    Scope t(GPUAR_SPAN_DECODE, (cudaStream_t)stream);
+    return ck(launch_decode(d_payload, c + GPUAR_PAD_BYTES, d_offsets, 0, (uint32_t)n_packets, d_out,
+                            (cudaStream_t)stream));
+}
+
+/* ----------------------------------------------------------------- profiling */
+void gpuar_b200_profile(int enable) { g_profile = enable != 0; }
+
+int gpuar_b200_profile_read(double ms[GPUAR_SPAN_COUNT], uint64_t calls[GPUAR_SPAN_COUNT])
+{
+    for (int k = 0; k < GPUAR_SPAN_COUNT; ++k) { ms[k] = 0; calls[k] = 0; }
+    cudaError_t bad = cudaSuccess;
+    for (const Span &s : g_spans) {
+        float t = 0;
+        cudaError_t e = cudaEventSynchronize(s.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, s.a, s.b);
+        if (e != cudaSuccess) bad = e;
+        else if (s.what >= 0 && s.what < GPUAR_SPAN_COUNT) { ms[s.what] += t; calls[s.what] += 1; }
+        g_event_pool.push_back(s.a);
+        g_event_pool.push_back(s.b);
+    }
+    g_spans.clear();
+    return ck(bad);
+}
+
+/* ------------------------------------------------------------------ header */
+void gpuar_b200_write_header(uint8_t hdr[20], uint64_t raw_bytes, uint64_t gip_bytes)
+{
+    memset(hdr, 0, GPUAR_FILE_HEADER);
+    hdr[0] = 0; hdr[1] = 1; hdr[2] = 0;                 /* file_header.hpp:25-27,33-35 */
+    for (int k = 0; k < 8; ++k) {
+        hdr[4 + k] = (uint8_t)(raw_bytes >> (8 * k));   /* :61-66 defines the low 4 bytes */
+        hdr[12 + k] = (uint8_t)(gip_bytes >> (8 * k));  /* :67-72 */
+    }
+}
+
+int gpuar_b200_check_header(const uint8_t hdr[20])
+{
+    return (hdr[0] == 0 && hdr[1] == 1 && hdr[2] == 0) ? 0 : GPUAR_E_FORMAT;   /* file_header.hpp:74-77 */
+}
+
+int gpuar_b200_gip_raw_size(const uint8_t *gip, size_t gip_bytes, uint64_t *raw_bytes)
+{
+    if (!gip || !raw_bytes || gip_bytes < GPUAR_FILE_HEADER) return GPUAR_E_FORMAT;
+    if (gpuar_b200_check_header(gip)) return GPUAR_E_FORMAT;
+    uint64_t lo = 0, hi = 0;
+    for (int k = 0; k < 4; ++k) {
+        lo |= (uint64_t)gip[4 + k] << (8 * k);
+        hi |= (uint64_t)gip[8 + k] << (8 * k);
+    }
+    /* bytes 8-11 are uninitialised in reference-written files: trust them only if the
+     * resulting size is plausible for this payload (each packet holds <= 8192 raw bytes
+     * and occupies >= 5 bytes) */
+    const uint64_t payload = gip_bytes - GPUAR_FILE_HEADER;
+    const uint64_t wide = lo | (hi << 32);
+    *raw_bytes = (hi && wide <= (payload / 5 + 1) * (uint64_t)kPacket) ? wide : lo;
+    return 0;
+}
+
+/* ------------------------------------------------ host-buffer entry points */
+int gpuar_b200_compress_host(const uint8_t *in, size_t n, uint8_t *gip, size_t gip_cap, size_t *gip_bytes)
+{
+    if (!gip || !gip_bytes || (n && !in)) return GPUAR_E_ARG;
+    if (gip_cap < GPUAR_FILE_HEADER + gpuar_b200_payload_bound(n)) return GPUAR_E_ARG;
+    std::lock_guard<std::mutex> lock(g_mu);
+    HostPath *h = nullptr;
+    int rc = host_path(&h);
+    if (rc) return rc;
+
+    // chunks of 2048 packets (16 MiB) rotate over kLanes streams: H2D, encode and
+    // scan+compact of chunk k overlap the D2H of chunk k-1; the host only waits for the
+    // 8-byte total of a chunk to know where the next one lands in the image
+    const size_t chunk = (size_t)2048 * kPacket;
+    const size_t chunks = (n + chunk - 1) / chunk;
+    size_t pos = GPUAR_FILE_HEADER;
+    cudaError_t e = cudaSuccess;
+    auto drain = [&](size_t k) -> cudaError_t {
+        const int l = (int)(k % kLanes);
+        cudaError_t er = cudaEventSynchronize(h->done[l]);
+        if (er != cudaSuccess) return er;
+        const size_t bytes = (size_t)h->h_total[l];
+        er = cudaMemcpyAsync(gip + pos, h->pay[l].p, bytes, cudaMemcpyDeviceToHost, h->stream[l]);
+        pos += bytes;
+        return er;
+    };
+    for (size_t k = 0; k < chunks && e == cudaSuccess; ++k) {
+        const int l = (int)(k % kLanes);
+        const size_t off = k * chunk, m = (n - off < chunk) ? n - off : chunk;
+        const EncodePlan p = encode_plan(m);
+        if (k >= (size_t)kLanes) e = drain(k - kLanes);            // frees lane l's buffers (stream order)
+        if (e == cudaSuccess) e = h->in[l].need(align_up(m, 16) + 16);
+        if (e == cudaSuccess) e = h->pay[l].need(gpuar_b200_payload_bound(m) + 16);
+        if (e == cudaSuccess) e = h->scratch[l].need(p.total);
+        if (e != cudaSuccess) break;
+        cudaStream_t st = h->stream[l];
+        e = cudaMemcpyAsync(h->in[l].p, in + off, m, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) break;
+        uint64_t *d_total = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(h->pay[l].p) +
+                                                         gpuar_b200_payload_bound(m));
+        rc = gpuar_b200_encode((const uint8_t *)h->in[l].p, m, (uint8_t *)h->pay[l].p, h->pay[l].cap, d_total,
+                               nullptr, h->scratch[l].p, h->scratch[l].cap, st);
+        if (rc) return rc;
+        e = cudaMemcpyAsync(&h->h_total[l], d_total, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaEventRecord(h->done[l], st);
+    }
+    for (size_t k = (chunks > (size_t)kLanes ? chunks - kLanes : 0); k < chunks && e == cudaSuccess; ++k)
+        e = drain(k);
+    for (int l = 0; l < kLanes && e == cudaSuccess; ++l) e = cudaStreamSynchronize(h->stream[l]);
+    if (e != cudaSuccess) return ck(e);
+    gpuar_b200_write_header(gip, n, pos);
+    *gip_bytes = pos;
+    return 0;
+}
+
+int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *out, size_t out_cap,
+                               size_t *out_bytes)
+{
+    if (!gip || !out_bytes) return GPUAR_E_ARG;
+    uint64_t raw = 0;
+    int rc = gpuar_b200_gip_raw_size(gip, gip_bytes, &raw);
+    if (rc) return rc;
+    const size_t c = gip_bytes - GPUAR_FILE_HEADER;
+    if (c == 0) { *out_bytes = 0; return 0; }
+    std::lock_guard<std::mutex> lock(g_mu);
+    HostPath *h = nullptr;
+    if ((rc = host_path(&h))) return rc;
+
+    // the header's size field is 32 bit in reference-written files; the chain is the truth.
+    // Upper bound on packets for buffer sizing: the caller's buffer.
+    const size_t max_packets = out_cap / kPacket + 1;
+    cudaError_t e = h->big_in.need(align_up(c, 16) + GPUAR_PAD_BYTES + 16);
+    if (e == cudaSuccess) e = h->big_scratch.need(index_scratch_bytes(c));
+    if (e == cudaSuccess) e = h->offsets.need(max_packets * 8);
+    if (e == cudaSuccess) e = h->result.need(64);
+    if (e == cudaSuccess) e = h->big_out.need(max_packets * (size_t)kPacket);
+    if (e != cudaSuccess) return ck(e);
+    cudaStream_t st = h->stream[0];
+    uint8_t *d_pay = (uint8_t *)h->big_in.p;
+    e = cudaMemsetAsync(d_pay + c, 0, GPUAR_PAD_BYTES, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_pay, gip + GPUAR_FILE_HEADER, c, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return ck(e);
+    rc = gpuar_b200_index(d_pay, c, (uint64_t *)h->offsets.p, max_packets, (uint64_t *)h->result.p,
+                          h->big_scratch.p, h->big_scratch.cap, st);
+    if (rc) return rc;
+    uint64_t *res = h->h_total + 8;
+    e = cudaMemcpyAsync(res, h->result.p, 32, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return ck(e);
+    if (res[2] != 0) return (int)(int64_t)res[2];
+    const size_t packets = (size_t)res[0], total = (size_t)res[1];
+    if ((uint32_t)raw != (uint32_t)total) return GPUAR_E_FORMAT;    // header field, file_header.hpp:61-66
+    if (total > out_cap || !out) return GPUAR_E_ARG;
+
+    // decode in packet ranges; the D2H of range k overlaps the decode of range k+1
+    const size_t step = 4096;                                       // packets per range (32 MiB)
+    for (size_t p0 = 0, k = 0; p0 < packets; p0 += step, ++k) {
+        const size_t m = (packets - p0 < step) ? packets - p0 : step;
+        uint8_t *d_out = (uint8_t *)h->big_out.p + p0 * kPacket;
+        rc = gpuar_b200_decode(d_pay, c, (const uint64_t *)h->offsets.p + p0, m, d_out, m * (size_t)kPacket, st);
+        if (rc) return rc;
+        e = cudaEventRecord(h->ready, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->copy, h->ready, 0);
+        const size_t lo = p0 * kPacket, hi = (lo + m * kPacket < total) ? lo + m * kPacket : total;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out + lo, d_out, hi - lo, cudaMemcpyDeviceToHost, h->copy);
+        if (e != cudaSuccess) return ck(e);
+    }
+    e = cudaStreamSynchronize(h->copy);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return ck(e);
+    *out_bytes = total;
+    return 0;
+}
+
+/* ------------------------------------------------------------ multi-GPU */
+int gpuar_b200_peer_concat(uint8_t *d_dst, int dst_device, size_t dst_offset, const uint8_t *d_src,
+                           int src_device, size_t bytes, void *stream)
+{
+    if (!bytes) return 0;
+    if (!d_dst || !d_src) return GPUAR_E_ARG;
+    return ck(cudaMemcpyPeerAsync(d_dst + dst_offset, dst_device, d_src, src_device, bytes, (cudaStream_t)stream));
+}
+
+int gpuar_b200_ipc_export(const void *d_ptr, uint8_t handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, const_cast<void *>(d_ptr));
+    if (e != cudaSuccess) return ck(e);
+    memcpy(handle, &hd, 64);
+    return 0;
+}
+
+int gpuar_b200_ipc_open(const uint8_t handle[64], void **d_ptr)
+{
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle, 64);
+    return ck(cudaIpcOpenMemHandle(d_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+}
+
+int gpuar_b200_ipc_close(void *d_ptr) { return ck(cudaIpcCloseMemHandle(d_ptr)); }
+
+/* ------------------------------------------- reference-named shims (gpuar.h:74,77-78) */
+void initConstantRange(void) { (void)gpuar_b200_init(); }
+
+void garCompressExecutor(const uint8_t *source, size_t size, uint8_t *destination, uint32_t numBlocks)
+{
+    (void)numBlocks;
+    (void)launch_encode_slots(source, size, destination, kSlot, nullptr, (cudaStream_t)0);
+}
+
+void garDecompressExecutor(const uint8_t *source, size_t size, uint8_t *destination, uint32_t numBlocks)
+{
+    (void)numBlocks;
+    (void)launch_decode(source, size, nullptr, kSlot, (uint32_t)(size / kSlot), destination, (cudaStream_t)0);
+}
+
+}  // extern "C"

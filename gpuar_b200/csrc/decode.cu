@@ -1,0 +1,130 @@
+// decode.cu -- sm_100a decode path, lane = packet.
+//
+// Replaces garDecompress / arDecompress (reference src/gpuar_kernel.cu:848-892,
+// 916-934).  Per symbol the reference does: getUnscaledCode (:703-716, a divide by
+// the current range), getSymbolFromProbability (:727-763, binary search over Fenwick
+// prefix sums, ~140 dependent shared loads), applySymbolRange (:256-288, two more
+// Fenwick sums + update) and readEncodedBits (:787-836, bit-at-a-time).
+//
+// Here the adaptive model of each packet is a 4-ary cumulative-count tree in shared
+// memory, interleaved so that lane l only ever touches bank pair (2l, 2l+1):
+//   level 0: 1 node  (children span 64 symbols)      node = 3 running thresholds
+//   level 1: 4 nodes (16)                            t0 = |child0|, t1 = t0+|child1|,
+//   level 2: 16 nodes (4)                            t2 = t1+|child2|   (u16 each)
+//   level 3: 64 nodes (1)
+// One descent (4 dependent 8-byte loads) finds the symbol, yields cum[s] and count[s]
+// and applies the model update (+1 on every threshold at or right of the path) in the
+// same pass.  Interval arithmetic and renormalisation are the closed forms of
+// common.cuh; bits come from a 64-bit reservoir fed by 32-bit loads one word ahead.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gpuar {
+
+__device__ __forceinline__ const uint32_t *clamp_ptr(const uint32_t *p, const uint32_t *last)
+{
+    return p < last ? p : last;          // reads past the buffer are pinned to its last word
+}
+
+struct DecShared {
+    TreeNode tree[kTreeNodes][32];   // 21760 B; lane l owns column l (banks 2l, 2l+1)
+};
+
+__global__ void __launch_bounds__(32)
+decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64_t *__restrict__ offsets,
+              uint32_t stride, uint32_t n_packets, uint8_t *__restrict__ out)
+{
+    __shared__ __align__(16) DecShared sm;
+    const uint32_t lane = lane_id();
+    const uint32_t my = blockIdx.x * 32u + lane;
+    const bool mine = my < n_packets;
+
+    // model init: every count 1 (gpuar_kernel.cu:403-419)
+    TreeNode *const tree = &sm.tree[0][lane];
+    tree_init(tree, 32u);
+
+    // bit source: aligned 32-bit words of the packet's bitstream, one word prefetched
+    const uint32_t *const wend = reinterpret_cast<const uint32_t *>(payload) + (readable >> 2) - 1;  // last readable word
+    const uint32_t *wp = wend;      // word held in `ahead`
+    uint32_t ahead = 0;             // prefetched word, big-endian (first stream bit = MSB)
+    BitSource in;
+    in.buf = 0;
+    in.have = 64u;
+    uint32_t raw = 0;
+    if (mine) {
+        const size_t off = offsets ? (size_t)offsets[my] : (size_t)my * stride;
+        const uint32_t hdr = (uint32_t)payload[off + 2] | ((uint32_t)payload[off + 3] << 8);   // rawLen, :859
+        raw = min(hdr, kPacket);
+        const size_t sp = off + kHdr;                              // first bitstream byte, any alignment
+        wp = reinterpret_cast<const uint32_t *>(payload) + (sp >> 2);
+        const uint32_t skip = 8u * (uint32_t)(sp & 3u);
+        in.buf = (uint64_t)bswap32(*clamp_ptr(wp, wend)) << (32u + skip);
+        in.have = 32u - skip;
+        ++wp;
+        in.feed(bswap32(*clamp_ptr(wp, wend)));                          // 40..64 bits
+        ++wp;
+        ahead = bswap32(*clamp_ptr(wp, wend));
+    }
+    // initializeDecoder (:582-603): the first 16 bits
+    uint32_t code = in.take(16u);
+    if (in.hungry()) {
+        in.feed(ahead);
+        ++wp;
+        ahead = bswap32(*clamp_ptr(wp, wend));
+    }
+    uint32_t L = 0, V = 0;
+
+    const uint32_t max_raw = __reduce_max_sync(kFull, raw);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)my * kPacket);
+    uint32_t packed = 0;
+
+    const uint32_t rounds = (max_raw + 31u) >> 5;
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint32_t i0 = r * 32u;
+        uint32_t sh_l;
+        const uint32_t m_l = magic_for(256u + i0 + lane, sh_l);    // lane j holds the divisor of step j
+#pragma unroll 4
+        for (uint32_t j = 0; j < 32u; ++j) {
+            const uint32_t m = __shfl_sync(kFull, m_l, j);
+            const uint32_t sh = __shfl_sync(kFull, sh_l, j);
+            const uint32_t i = i0 + j;
+            if (i < raw) {
+                const uint32_t T = 256u + i;
+                const uint32_t target = unscale(code, L, V, T);
+                uint32_t lo, cnt;
+                const uint32_t s = tree_decode(tree, 32u, target, T, lo, cnt);
+                packed |= s << (8u * (j & 3u));
+                uint32_t k, u, U1;
+                narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
+                code = advance_code(code, k, u, in);
+                if (in.hungry()) {
+                    in.feed(ahead);
+                    ++wp;
+                    ahead = bswap32(*clamp_ptr(wp, wend));
+                }
+            }
+            if ((j & 3u) == 3u) {
+                if (mine && (i & ~3u) < raw) {
+                    if (i < raw) {
+                        dst[i >> 2] = packed;
+                    } else {                                       // ragged tail of the last packet
+                        uint8_t *b = reinterpret_cast<uint8_t *>(dst) + (i & ~3u);
+                        for (uint32_t q = 0; q < (raw & 3u); ++q) b[q] = (uint8_t)(packed >> (8u * q));
+                    }
+                }
+                packed = 0;
+            }
+        }
+    }
+}
+
+cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint64_t *d_offsets, uint32_t stride,
+                          uint32_t packets, uint8_t *d_out, cudaStream_t st)
+{
+    if (!packets) return cudaSuccess;
+    decode_kernel<<<(packets + 31u) / 32u, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace gpuar

@@ -1,0 +1,333 @@
+// index.cu -- packet-chain discovery on the device.
+//
+// The .gip payload stores no index: packet i+1 is found by adding compLen(i) to the
+// offset of packet i (reference src/cpu_compressor.cpp:50-56; the reference GPU driver
+// walks the chain on the host while reading the file, src/gpu_compressor.cpp:294-320).
+// A serial walk costs one dependent memory access per packet, so here it is parallel:
+//
+//   1. mark   every byte offset o is tested for "could start a packet":
+//             5 <= compLen <= 8704, o + compLen <= C, and rawLen == 8192 -- or the packet
+//             ends exactly at C (the last packet may be short).  Compressed data looks
+//             random, so false candidates are ~C/500k; true starts always qualify.
+//   2. emit   single-pass decoupled-look-back scan over the candidate bitmap writes the
+//             sorted candidate list cand[0..N).
+//   3. link   next[i] = position in cand[] of cand[i] + compLen(cand[i])   (galloping
+//             search; TERMINAL if it equals C, DEAD if it is not a candidate).
+//   4. lift   jump tables S_l = next^(32^l) for l = 1..top, each from the previous by a
+//             32-hop walk.
+//   5. finish one thread descends the tables from cand[0] = 0 to count the chain (P packets)
+//             and to validate that it ends at C.
+//   6. rank   thread r walks the tables along the base-32 digits of r: offsets[r].
+//
+// If the fast path cannot be used (too many candidates for the scratch, chain not
+// reaching C) step 5 falls back to a serial walk, which also validates the stream.
+#include "common.cuh"
+#include "kernels.h"
+#include "lookback.cuh"
+
+namespace gpuar {
+
+constexpr uint32_t kMarkThreads = 256;
+constexpr uint32_t kEmitThreads = 256;
+constexpr uint32_t kEmitWordsPerThread = 8;
+constexpr uint32_t kEmitTileWords = kEmitThreads * kEmitWordsPerThread;   // 2048 words = 64 KiB of payload
+constexpr uint32_t kMaxLevels = 7;                                        // 32^7 > 2^32 candidates
+
+struct IndexPlan {
+    size_t c;
+    size_t words;        // bitmap words
+    size_t tiles;        // emit tiles
+    uint32_t cap;        // candidate capacity; sentinels live at cap (TERMINAL) and cap+1 (DEAD)
+    uint32_t levels;     // jump tables S_0 .. S_{levels-1}
+    // scratch layout (byte offsets)
+    size_t off_bitmap, off_desc, off_cand, off_jump, off_ctl, total;
+};
+
+struct IndexCtl {        // device control block
+    uint32_t n_cand;     // candidates found (may exceed cap: then the fast path is off)
+    uint32_t serial;     // 1 = offsets were produced by the serial fallback
+};
+
+static IndexPlan make_plan(size_t c)
+{
+    IndexPlan p{};
+    p.c = c;
+    p.words = (c + 31) / 32;
+    p.tiles = (p.words + kEmitTileWords - 1) / kEmitTileWords;
+    // every-count-1 packets of zeros are 210 bytes: c/200 covers any stream this codec emits
+    const size_t cap = c / 200 + 4096;
+    p.cap = (uint32_t)(cap > 0xFFFFFFF0u ? 0xFFFFFFF0u : cap);
+    p.levels = 1;
+    for (uint64_t span = 32; span < (uint64_t)p.cap + 1 && p.levels < kMaxLevels; span *= 32) ++p.levels;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
+    p.off_bitmap = take((p.words + 8) * 4);
+    p.off_desc = take((p.tiles + 2) * 8);
+    p.off_cand = take(((size_t)p.cap + 2) * 8);
+    p.off_jump = take((size_t)p.levels * ((size_t)p.cap + 2) * 4);
+    p.off_ctl = take(sizeof(IndexCtl));
+    p.total = o;
+    return p;
+}
+
+size_t index_scratch_bytes(size_t c) { return make_plan(c).total; }
+
+__device__ __forceinline__ uint32_t ld16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+// ---- 1. mark: thread = 32 consecutive offsets = one bitmap word
+__global__ void __launch_bounds__(kMarkThreads)
+index_mark_kernel(const uint8_t *__restrict__ payload, size_t c, uint32_t *__restrict__ bitmap, size_t words)
+{
+    const size_t w = (size_t)blockIdx.x * kMarkThreads + threadIdx.x;
+    if (w >= words) return;
+    const size_t o0 = w * 32;
+    // bytes o0 .. o0+34 (payload is readable GPUAR_PAD_BYTES past c; base is 16-byte aligned)
+    const uint4 *v = reinterpret_cast<const uint4 *>(payload + o0);
+    const uint4 a = v[0], b = v[1];
+    const uint32_t tail = *reinterpret_cast<const uint32_t *>(payload + o0 + 32);
+    const uint32_t x[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, tail};
+    uint32_t bits = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 32; ++j) {
+        const uint32_t q = j >> 2, s = (j & 3u) * 8u;
+        const uint32_t four = __funnelshift_r(x[q], x[q + 1], s);   // bytes o..o+3
+        const uint32_t len = four & 0xFFFFu, raw = four >> 16;
+        const size_t o = o0 + j;
+        bool ok = len > kHdr && len <= kSlot && o + len <= c;
+        ok = ok && (raw == kPacket || (o + len == c && raw >= 1u && raw <= kPacket));
+        bits |= (uint32_t)ok << j;
+    }
+    bitmap[w] = bits;
+}
+
+// ---- 2. emit: ordered compaction of the set bits into cand[]
+__global__ void __launch_bounds__(kEmitThreads)
+index_emit_kernel(const uint32_t *__restrict__ bitmap, size_t words, uint64_t *__restrict__ cand, uint32_t cap,
+                  uint64_t *__restrict__ desc, uint32_t *__restrict__ ticket, IndexCtl *__restrict__ ctl,
+                  size_t tiles)
+{
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[kEmitThreads / 32];
+    __shared__ uint64_t s_base;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+
+    const size_t w0 = (size_t)tile * kEmitTileWords + (size_t)threadIdx.x * kEmitWordsPerThread;
+    uint32_t bm[kEmitWordsPerThread];
+    uint32_t mine = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kEmitWordsPerThread; ++k) {
+        bm[k] = (w0 + k < words) ? bitmap[w0 + k] : 0u;
+        mine += __popc(bm[k]);
+    }
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, inc, d);
+        if (lane >= (uint32_t)d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = lane < kEmitThreads / 32 ? s_warp[lane] : 0u;
+        uint32_t wi = v;
+#pragma unroll
+        for (int d = 1; d < (int)(kEmitThreads / 32); d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, wi, d);
+            if (lane >= (uint32_t)d) wi += t;
+        }
+        const uint32_t total = __shfl_sync(kFull, wi, kEmitThreads / 32 - 1);
+        if (lane < kEmitThreads / 32) s_warp[lane] = wi - v;       // exclusive warp bases
+        const uint64_t base = lookback_exclusive(desc, tile, total, lane);
+        if (lane == 0) {
+            s_base = base;
+            if ((size_t)tile + 1 == tiles) {
+                const uint64_t n = base + total;
+                ctl->n_cand = n > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)n;
+            }
+        }
+    }
+    __syncthreads();
+    uint64_t at = s_base + s_warp[warp] + (inc - mine);
+#pragma unroll
+    for (uint32_t k = 0; k < kEmitWordsPerThread; ++k) {
+        uint32_t b = bm[k];
+        while (b) {
+            const uint32_t j = __ffs(b) - 1u;
+            b &= b - 1u;
+            if (at < cap) cand[at] = (uint64_t)(w0 + k) * 32u + j;
+            ++at;
+        }
+    }
+}
+
+// ---- 3. link
+__global__ void __launch_bounds__(256)
+index_link_kernel(const uint8_t *__restrict__ payload, size_t c, const uint64_t *__restrict__ cand, uint32_t cap,
+                  const IndexCtl *__restrict__ ctl, uint32_t *__restrict__ jump, uint32_t levels)
+{
+    const uint32_t n = ctl->n_cand;
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t kTerminal = cap, kDead = cap + 1u;
+    if (i < 2u) {                                                   // sentinels of every table: self loops
+        for (uint32_t l = 0; l < levels; ++l) jump[(size_t)l * (cap + 2u) + cap + i] = cap + i;
+    }
+    if (n > cap || i >= n) return;
+    const uint64_t o = cand[i];
+    const uint64_t tgt = o + ld16(payload + o);
+    uint32_t nx = kDead;
+    if (tgt == c) {
+        nx = kTerminal;
+    } else {
+        // cand[] is sorted and tgt > o: gallop forward from i+1, then bisect
+        uint32_t lo = i + 1u, step = 1u;
+        uint32_t hi = lo;
+        while (hi < n && cand[hi] < tgt) { lo = hi + 1u; hi += step; step <<= 1; }
+        if (hi > n) hi = n;
+        while (lo < hi) {                                           // first index with cand >= tgt in [lo, hi)
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (cand[mid] < tgt) lo = mid + 1u; else hi = mid;
+        }
+        if (lo < n && cand[lo] == tgt) nx = lo;
+    }
+    jump[i] = nx;
+}
+
+// ---- 4. lift: S_l[i] = S_{l-1} applied 32 times
+__global__ void __launch_bounds__(256)
+index_lift_kernel(const uint32_t *__restrict__ prev, uint32_t *__restrict__ next, uint32_t cap,
+                  const IndexCtl *__restrict__ ctl)
+{
+    const uint32_t n = ctl->n_cand;
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (n > cap || i >= n) return;
+    uint32_t pos = i;
+#pragma unroll 1
+    for (int h = 0; h < 32 && pos < cap; ++h) pos = prev[pos];
+    next[i] = pos;
+}
+
+// ---- 5. finish: chain length + validation, or the serial fallback
+__global__ void index_finish_kernel(const uint8_t *__restrict__ payload, size_t c, const uint64_t *__restrict__ cand,
+                                    uint32_t cap, IndexCtl *__restrict__ ctl, const uint32_t *__restrict__ jump,
+                                    uint32_t levels, uint64_t *__restrict__ offsets, size_t max_packets,
+                                    uint64_t *__restrict__ result)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    ctl->serial = 0;
+    if (c == 0) {
+        result[0] = 0; result[1] = 0; result[2] = 0; result[3] = 0;
+        return;
+    }
+    const uint32_t n = ctl->n_cand;
+    const size_t row = (size_t)cap + 2u;
+    if (n && n <= cap && cand[0] == 0) {
+        uint32_t pos = 0;
+        uint64_t hops = 0, weight = 1;
+        for (uint32_t l = 1; l < levels; ++l) weight *= 32u;
+        for (int l = (int)levels - 1; l >= 0; --l, weight /= 32u) {
+            const uint32_t *S = jump + (size_t)l * row;
+            for (;;) {
+                const uint32_t nx = S[pos];
+                if (nx >= cap) break;
+                pos = nx;
+                hops += weight;
+            }
+        }
+        if (jump[pos] == cap) {                                     // last packet ends exactly at C
+            const uint64_t packets = hops + 1u;
+            const uint64_t last_raw = ld16(payload + cand[pos] + 2);
+            result[0] = packets;
+            result[1] = (packets - 1u) * kPacket + last_raw;
+            result[2] = packets <= max_packets ? 0ull : (uint64_t)(int64_t)-1;   // GPUAR_E_ARG
+            result[3] = n;
+            return;
+        }
+    }
+    // serial fallback: walk and validate (cpu_compressor.cpp:47-78)
+    ctl->serial = 1;
+    uint64_t o = 0, k = 0, raw_total = 0;
+    int64_t status = 0;
+    while (o < c) {
+        if (c - o < kHdr) { status = -2; break; }
+        const uint64_t len = ld16(payload + o), raw = ld16(payload + o + 2);
+        if (len <= kHdr || len > c - o) { status = -2; break; }
+        if (raw == 0 || raw > kPacket || (raw != kPacket && o + len != c)) { status = -4; break; }
+        if (k < max_packets) offsets[k] = o; else status = -1;
+        ++k;
+        raw_total += raw;
+        o += len;
+    }
+    result[0] = k;
+    result[1] = raw_total;
+    result[2] = (uint64_t)status;
+    result[3] = n;
+}
+
+// ---- 6. rank
+__global__ void __launch_bounds__(256)
+index_rank_kernel(const uint64_t *__restrict__ cand, uint32_t cap, const IndexCtl *__restrict__ ctl,
+                  const uint32_t *__restrict__ jump, uint32_t levels, uint64_t *__restrict__ offsets,
+                  size_t max_packets, const uint64_t *__restrict__ result)
+{
+    if (ctl->serial || result[2] != 0) return;
+    const uint64_t packets = result[0];
+    const uint64_t r = (uint64_t)blockIdx.x * 256u + threadIdx.x;
+    if (r >= packets || r >= max_packets) return;
+    const size_t row = (size_t)cap + 2u;
+    uint32_t pos = 0;
+    for (int l = (int)levels - 1; l >= 0; --l) {
+        const uint32_t *S = jump + (size_t)l * row;
+        const uint32_t digit = (uint32_t)(r >> (5 * l)) & 31u;
+        for (uint32_t h = 0; h < digit; ++h) pos = S[pos];
+    }
+    offsets[r] = cand[pos];
+}
+
+cudaError_t launch_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets, size_t max_packets,
+                         uint64_t *d_result, void *d_scratch, size_t scratch_bytes, cudaStream_t st)
+{
+    const IndexPlan p = make_plan(c);
+    if (scratch_bytes < p.total) return cudaErrorInvalidValue;
+    uint8_t *s = static_cast<uint8_t *>(d_scratch);
+    uint32_t *bitmap = reinterpret_cast<uint32_t *>(s + p.off_bitmap);
+    uint64_t *desc = reinterpret_cast<uint64_t *>(s + p.off_desc);
+    uint32_t *ticket = reinterpret_cast<uint32_t *>(desc + p.tiles);
+    uint64_t *cand = reinterpret_cast<uint64_t *>(s + p.off_cand);
+    uint32_t *jump = reinterpret_cast<uint32_t *>(s + p.off_jump);
+    IndexCtl *ctl = reinterpret_cast<IndexCtl *>(s + p.off_ctl);
+
+    cudaError_t e = cudaMemsetAsync(desc, 0, (p.tiles + 2) * 8, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(ctl, 0, sizeof(IndexCtl), st);
+    if (e != cudaSuccess) return e;
+    if (c) {
+        index_mark_kernel<<<(unsigned)((p.words + kMarkThreads - 1) / kMarkThreads), kMarkThreads, 0, st>>>(
+            d_payload, c, bitmap, p.words);
+        index_emit_kernel<<<(unsigned)p.tiles, kEmitThreads, 0, st>>>(bitmap, p.words, cand, p.cap, desc, ticket,
+                                                                      ctl, p.tiles);
+        // candidates of a well-formed stream: one per packet plus ~c/500k false ones; the grid
+        // covers the whole capacity and threads past n_cand exit
+        const unsigned grid = (unsigned)(((size_t)p.cap + 255) / 256);
+        index_link_kernel<<<grid, 256, 0, st>>>(d_payload, c, cand, p.cap, ctl, jump, p.levels);
+        for (uint32_t l = 1; l < p.levels; ++l)
+            index_lift_kernel<<<grid, 256, 0, st>>>(jump + (size_t)(l - 1) * ((size_t)p.cap + 2),
+                                                    jump + (size_t)l * ((size_t)p.cap + 2), p.cap, ctl);
+        count_launch(3 + (int)p.levels - 1);
+    }
+    index_finish_kernel<<<1, 32, 0, st>>>(d_payload, c, cand, p.cap, ctl, jump, p.levels, d_offsets, max_packets,
+                                          d_result);
+    count_launch();
+    if (c) {
+        // at most one packet per 5 payload bytes; well-formed streams have far fewer
+        const size_t upper = max_packets < c / 5 + 1 ? max_packets : c / 5 + 1;
+        index_rank_kernel<<<(unsigned)((upper + 255) / 256), 256, 0, st>>>(cand, p.cap, ctl, jump, p.levels,
+                                                                           d_offsets, max_packets, d_result);
+        count_launch();
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace gpuar

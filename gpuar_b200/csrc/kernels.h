@@ -1,0 +1,27 @@
+// kernels.h -- host-side launchers of the codec kernels (internal to libgpuar_b200.so)
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gpuar {
+
+// encode.cu
+const void *probe_kernel();   // address of a kernel of this library, for image-loadability checks
+cudaError_t launch_encode_slots(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t slot_stride,
+                                uint32_t *d_sizes, cudaStream_t st);
+size_t compact_desc_bytes(size_t packets);
+cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const uint32_t *d_sizes,
+                           uint32_t packets, uint8_t *d_payload, uint64_t *d_desc, uint64_t *d_total,
+                           cudaStream_t st);
+
+// decode.cu: d_offsets == nullptr means packet p starts at p * stride (reference slot layout)
+cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint64_t *d_offsets, uint32_t stride,
+                          uint32_t packets, uint8_t *d_out, cudaStream_t st);
+
+// index.cu
+size_t index_scratch_bytes(size_t c);
+cudaError_t launch_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets, size_t max_packets,
+                         uint64_t *d_result, void *d_scratch, size_t scratch_bytes, cudaStream_t st);
+
+}  // namespace gpuar

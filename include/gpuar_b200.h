@@ -1,0 +1,153 @@
+/*
+ * gpuar_b200.h -- C ABI of the B200 (sm_100a) GPUAR codec library, libgpuar_b200.so.
+ *
+ * This is the drop-in boundary for the reference's device codec seam:
+ *   - the `extern "C"` block of the reference,           src/gpuar.h:59-86
+ *   - its constants,                                      src/gpu.h:8-14
+ *   - and the device work the reference's host driver does around it
+ *     (host-side compaction of fixed-stride slots, gpu_compressor.cpp:136-169, and
+ *     the host-side packet-chain walk, gpu_compressor.cpp:294-320), which here
+ *     run on the device.
+ *
+ * Plain pointers and sizes only.  Every `d_` pointer is device memory on the
+ * CURRENT CUDA device (cudaSetDevice is the caller's business, as in the
+ * reference); `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ * stream).  All device entry points are asynchronous with respect to the host
+ * unless stated otherwise; results written to device memory are valid after
+ * the stream has been synchronised.  Return value: 0 = ok, > 0 = a cudaError_t,
+ * < 0 = one of the GPUAR_E_* codes below.  There is no CPU fallback anywhere in
+ * this library: with no usable device every entry point fails.
+ *
+ * Wire format (identical to the reference):
+ *   .gip    = 20-byte header | payload
+ *   payload = packets tightly concatenated in input order
+ *   packet  = u16 LE compLen (incl. these 4 bytes) | u16 LE rawLen | bitstream
+ *   rawLen  = 8192 for every packet except possibly the last.
+ */
+#ifndef GPUAR_B200_H
+#define GPUAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* format constants -- src/gpu.h:8-14, src/file_header.hpp:19-22 */
+#define GPUAR_PACKET_BYTES 8192u  /* UNCOMPRESSED_PACKET_SIZE */
+#define GPUAR_SLOT_BYTES 8704u    /* COMPRESSED_PACKET_SIZE   */
+#define GPUAR_PACKET_HEADER 4u    /* PACKET_HEADER_LENGTH     */
+#define GPUAR_FILE_HEADER 20u     /* FileHeader::HEADER_LENGTH */
+#define GPUAR_PAD_BYTES 64u       /* readable slack required past a payload (decoder over-read) */
+
+#define GPUAR_E_ARG (-1)          /* bad argument / buffer too small            */
+#define GPUAR_E_FORMAT (-2)       /* malformed .gip header or packet chain      */
+#define GPUAR_E_NODEVICE (-3)     /* no CUDA device / kernel image not loadable */
+#define GPUAR_E_UNSUPPORTED (-4)  /* valid but outside what the device path handles */
+
+int gpuar_b200_abi_version(void);
+const char *gpuar_b200_strerror(int code);
+
+/* Once per device before any other call (replaces initConstantRange, gpuar.h:74):
+ * uploads the per-position reciprocal table.  Synchronous. */
+int gpuar_b200_init(void);
+
+/* ---------------------------------------------------------------- sizing */
+size_t gpuar_b200_packets(size_t n);              /* ceil(n / 8192)                              */
+size_t gpuar_b200_payload_bound(size_t n);        /* packets * 8704 + GPUAR_PAD_BYTES            */
+size_t gpuar_b200_encode_scratch_bytes(size_t n); /* device scratch for gpuar_b200_encode        */
+size_t gpuar_b200_index_scratch_bytes(size_t c);  /* device scratch for gpuar_b200_index         */
+
+/* ---------------------------------------------------------------- encode
+ * d_in[n] -> d_payload (packets compacted on the device, no 20-byte header).
+ * Replaces garCompressExecutor (gpuar.h:77) + the per-packet D2H/fwrite loop
+ * (gpu_compressor.cpp:136-169).
+ *   d_in            16-byte aligned.
+ *   d_payload       16-byte aligned, capacity >= gpuar_b200_payload_bound(n).
+ *   d_payload_bytes device u64: total payload length C.
+ *   d_packet_sizes  optional device u32[packets]: compLen of each packet (may be NULL).
+ */
+int gpuar_b200_encode(const uint8_t *d_in, size_t n, uint8_t *d_payload, size_t payload_cap,
+                      uint64_t *d_payload_bytes, uint32_t *d_packet_sizes, void *d_scratch,
+                      size_t scratch_bytes, void *stream);
+
+/* ---------------------------------------------------------------- index
+ * Packet-chain discovery on the device (the format stores no index).  Replaces
+ * the host chain walk of gpu_compressor.cpp:294-320.
+ *   d_payload     16-byte aligned, c payload bytes, readable to c + GPUAR_PAD_BYTES.
+ *   d_offsets     device u64[max_packets]: byte offset of each packet in d_payload.
+ *   d_result      device u64[4]: [0] packet count, [1] total rawLen, [2] status
+ *                 (0 ok, else a GPUAR_E_* code as two's complement), [3] reserved.
+ * max_packets >= c/5 + 1 is always enough; >= ceil(raw/8192) suffices for well-formed input.
+ */
+int gpuar_b200_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets, size_t max_packets,
+                     uint64_t *d_result, void *d_scratch, size_t scratch_bytes, void *stream);
+
+/* ---------------------------------------------------------------- decode
+ * Packets at d_offsets[0..n_packets) -> d_out; packet p is written at p * 8192
+ * (gpuar_kernel.cu:924).  Replaces garDecompressExecutor (gpuar.h:78).
+ *   d_out  16-byte aligned, capacity >= n_packets * 8192.
+ */
+int gpuar_b200_decode(const uint8_t *d_payload, size_t c, const uint64_t *d_offsets, size_t n_packets,
+                      uint8_t *d_out, size_t out_cap, void *stream);
+
+/* ------------------------------------------------- host-buffer entry points
+ * Whole .gip image in host memory <-> raw bytes in host memory on the current
+ * device: staging, H2D, kernels, D2H, header.  Synchronous.  What a caller of
+ * the reference's GPUCompressor::compress/decompress gets, minus the file I/O.
+ * `gip_cap` >= 20 + gpuar_b200_payload_bound(n).
+ */
+int gpuar_b200_compress_host(const uint8_t *in, size_t n, uint8_t *gip, size_t gip_cap, size_t *gip_bytes);
+int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *out, size_t out_cap,
+                               size_t *out_bytes);
+/* raw size announced by a .gip image (walks nothing: header field, 32-bit in the
+ * reference's layout, 64-bit when written by this library -- see DESIGN.md). */
+int gpuar_b200_gip_raw_size(const uint8_t *gip, size_t gip_bytes, uint64_t *raw_bytes);
+
+/* 20-byte header, byte-compatible with file_header.hpp:28-36,61-72 in every byte the
+ * reference defines; the bytes it leaves uninitialised carry the high halves of the
+ * 64-bit sizes (zero below 4 GiB). */
+void gpuar_b200_write_header(uint8_t hdr[20], uint64_t raw_bytes, uint64_t gip_bytes);
+int gpuar_b200_check_header(const uint8_t hdr[20]);
+
+/* --------------------------------------------- multi-GPU stream concatenation
+ * Peer copy of one rank's compacted payload into the gathered payload that lives
+ * on another device of the same box (NVLink): dst_device/dst may be a
+ * cudaIpcOpenMemHandle mapping.  Asynchronous on `stream`. */
+int gpuar_b200_peer_concat(uint8_t *d_dst, int dst_device, size_t dst_offset, const uint8_t *d_src,
+                           int src_device, size_t bytes, void *stream);
+int gpuar_b200_ipc_export(const void *d_ptr, uint8_t handle[64]);
+int gpuar_b200_ipc_open(const uint8_t handle[64], void **d_ptr);
+int gpuar_b200_ipc_close(void *d_ptr);
+
+/* --------------------------------------------------- reference-named shims
+ * Same names, signatures and slot layout as src/gpuar.h:74,77-78, so the
+ * reference's gpu_compressor.cpp links against this library unchanged:
+ * packet t is read at d_src + t*8192 and written to d_dst + t*8704 (encode),
+ * or read at d_src + t*8704 and written to d_dst + t*8192 (decode); launched on
+ * the legacy default stream; numBlocks is accepted and ignored (the grid is
+ * derived from size). */
+void initConstantRange(void);
+void garCompressExecutor(const uint8_t *source, size_t size, uint8_t *destination, uint32_t numBlocks);
+void garDecompressExecutor(const uint8_t *source, size_t size, uint8_t *destination, uint32_t numBlocks);
+
+/* ----------------------------------------------------------- measurement hooks
+ * gpuar_b200_profile(1) makes encode/index/decode record CUDA events on the caller's
+ * stream around each kernel group; gpuar_b200_profile_read waits for the recorded spans,
+ * returns accumulated milliseconds and span counts per group, and clears them. */
+#define GPUAR_SPAN_ENCODE 0   /* model + coder kernel                     */
+#define GPUAR_SPAN_COMPACT 1  /* size scan + stream compaction kernel     */
+#define GPUAR_SPAN_INDEX 2    /* packet-chain discovery kernels           */
+#define GPUAR_SPAN_DECODE 3   /* decode kernel                            */
+#define GPUAR_SPAN_COUNT 4
+void gpuar_b200_profile(int enable);
+int gpuar_b200_profile_read(double ms[GPUAR_SPAN_COUNT], uint64_t calls[GPUAR_SPAN_COUNT]);
+
+/* launch counter: number of this library's kernels launched since load (bench.py's gpu_launches) */
+uint64_t gpuar_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUAR_B200_H */

@@ -1,0 +1,175 @@
+// host_model.cpp -- CPU emulation of the CUDA kernels' data flow, built with g++ from the
+// SAME arithmetic source the kernels use (gpuar_b200/csrc/coder_math.h).  Test
+// infrastructure: it lets `pytest -m "not gpu"` check the closed forms (reciprocal
+// division, renormalisation, bit packing, packed-u16 scans, ballot ranks, the 4-ary
+// model tree, the float-estimated divide) against the oracle without a GPU.  The warp
+// is emulated lane by lane; ballots and shuffles become loops over 32 lanes.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../gpuar_b200/csrc/coder_math.h"
+
+using namespace gpuar;
+
+namespace {
+
+// model pass of encode_kernel for one packet: pair[i] = lo | cnt << 16
+void model_pass(const uint8_t *x, uint32_t n, std::vector<uint32_t> &pair)
+{
+    uint16_t cnt[256], pre[256];
+    for (int s = 0; s < 256; ++s) { cnt[s] = 1; pre[s] = (uint16_t)s; }
+    pair.resize(n);
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+        const uint32_t valid = n - i0 < 32 ? n - i0 : 32;
+        const uint32_t amask = valid == 32 ? 0xFFFFFFFFu : ((1u << valid) - 1u);
+        uint32_t sym[32], E[32], LT[32];
+        for (uint32_t l = 0; l < 32; ++l) { sym[l] = l < valid ? x[i0 + l] : 0; E[l] = amask; LT[l] = 0; }
+        for (int b = 7; b >= 0; --b) {
+            uint32_t B = 0;                                        // __ballot_sync(bit && act)
+            for (uint32_t l = 0; l < 32; ++l) B |= (uint32_t)(((sym[l] >> b) & 1u) && l < valid) << l;
+            for (uint32_t l = 0; l < 32; ++l) {
+                if ((sym[l] >> b) & 1u) { LT[l] |= E[l] & ~B; E[l] &= B; }
+                else E[l] &= ~B;
+            }
+        }
+        uint16_t newcnt[256];
+        memcpy(newcnt, cnt, sizeof cnt);
+        for (uint32_t l = 0; l < valid; ++l) {
+            const uint32_t ltmask = (1u << l) - 1u;
+            const uint32_t lo = pre[sym[l]] + (uint32_t)__builtin_popcount(LT[l] & ltmask);
+            const uint32_t c = cnt[sym[l]] + (uint32_t)__builtin_popcount(E[l] & ltmask);
+            pair[i0 + l] = lo | (c << 16);
+            if ((E[l] >> l) == 1u) newcnt[sym[l]] = (uint16_t)(cnt[sym[l]] + __builtin_popcount(E[l]));
+        }
+        memcpy(cnt, newcnt, sizeof cnt);
+        // packed rescan: lane l owns bins 8l..8l+7
+        uint32_t tot[32], e[32][4];
+        for (uint32_t l = 0; l < 32; ++l) {
+            uint32_t c[4];
+            memcpy(c, &cnt[8 * l], 16);
+            tot[l] = prefix8_packed(c, e[l]);
+        }
+        uint32_t run = 0;
+        for (uint32_t l = 0; l < 32; ++l) {
+            const uint32_t base = run * 0x10001u;
+            uint32_t w[4] = {e[l][0] + base, e[l][1] + base, e[l][2] + base, e[l][3] + base};
+            memcpy(&pre[8 * l], w, 16);
+            run += tot[l];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// encode one packet exactly as a lane of encode_kernel does; returns compLen
+uint32_t host_model_encode_packet(const uint8_t *x, uint32_t n, uint8_t *slot, uint32_t slot_bytes)
+{
+    std::vector<uint32_t> pair;
+    model_pass(x, n, pair);
+    uint32_t L = 0, V = 0, pend = 0;
+    BitSink out;
+    out.acc = 0;
+    out.nb = 0;
+    out.wp = reinterpret_cast<uint32_t *>(slot + kHdr);
+    out.end = reinterpret_cast<uint32_t *>(slot + (slot_bytes & ~3u));
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t sh;
+        const uint32_t m = magic_for(256u + i, sh);
+        const uint32_t lo = pair[i] & 0xFFFFu, hi = lo + (pair[i] >> 16);
+        uint32_t k, u, U1;
+        narrow_renorm(L, V, lo, hi, m, sh, k, u, U1);
+        emit_symbol(out, pend, k, u, U1);
+    }
+    return finish_packet(out, L, pend, slot, n);
+}
+
+size_t host_model_encode_stream(const uint8_t *in, size_t n, uint8_t *payload)
+{
+    std::vector<uint8_t> slot(kSlot + 16);
+    size_t pos = 0;
+    for (size_t off = 0; off < n; off += kPacket) {
+        const uint32_t m = (uint32_t)(n - off < kPacket ? n - off : kPacket);
+        const uint32_t len = host_model_encode_packet(in + off, m, slot.data(), kSlot);
+        memcpy(payload + pos, slot.data(), len);
+        pos += len;
+    }
+    return pos;
+}
+
+// decode the packet at byte offset `off` of a padded, 4-byte aligned payload exactly as a
+// lane of decode_kernel does; returns bytes produced
+uint32_t host_model_decode_packet(const uint8_t *payload, size_t readable, size_t off, uint8_t *out)
+{
+    std::vector<TreeNode> tree(kTreeNodes);
+    tree_init(tree.data(), 1);
+    const uint32_t *const words = reinterpret_cast<const uint32_t *>(payload);
+    const uint32_t *const wend = words + (readable >> 2) - 1;
+    auto word = [&](const uint32_t *p) { return bswap32(*(p < wend ? p : wend)); };
+    const uint32_t raw = (uint32_t)payload[off + 2] | ((uint32_t)payload[off + 3] << 8);
+    const size_t sp = off + kHdr;
+    const uint32_t *wp = words + (sp >> 2);
+    const uint32_t skip = 8u * (uint32_t)(sp & 3u);
+    BitSource in;
+    in.buf = (uint64_t)word(wp) << (32u + skip);
+    in.have = 32u - skip;
+    ++wp;
+    in.feed(word(wp));
+    ++wp;
+    uint32_t ahead = word(wp);
+    uint32_t code = in.take(16u);
+    if (in.hungry()) { in.feed(ahead); ++wp; ahead = word(wp); }
+    uint32_t L = 0, V = 0;
+    for (uint32_t i = 0; i < raw && i < kPacket; ++i) {
+        const uint32_t T = 256u + i;
+        uint32_t sh;
+        const uint32_t m = magic_for(T, sh);
+        const uint32_t target = unscale(code, L, V, T);
+        uint32_t lo, cnt;
+        const uint32_t s = tree_decode(tree.data(), 1, target, T, lo, cnt);
+        out[i] = (uint8_t)s;
+        uint32_t k, u, U1;
+        narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
+        code = advance_code(code, k, u, in);
+        if (in.hungry()) { in.feed(ahead); ++wp; ahead = word(wp); }
+    }
+    return raw < kPacket ? raw : kPacket;
+}
+
+// exhaustive-ish check of the reciprocal division: for every total T and for numerators
+// around every multiple of T up to max_n (plus random ones): returns the number of mismatches
+uint64_t host_model_check_division(uint32_t max_n)
+{
+    uint64_t bad = 0;
+    for (uint32_t T = 256; T < 256 + kPacket; ++T) {
+        uint32_t sh;
+        const uint32_t m = magic_for(T, sh);
+        for (uint64_t q = 0; q * T <= max_n; q += 1 + q / 64) {
+            for (int d = -1; d <= 1; ++d) {
+                const int64_t n = (int64_t)(q * T) + d;
+                if (n < 0 || n > max_n) continue;
+                bad += div_total((uint32_t)n, m, sh) != (uint32_t)n / T;
+            }
+        }
+        bad += div_total(max_n, m, sh) != max_n / T;
+    }
+    return bad;
+}
+
+// the float-estimated divide of the decoder against integer division, on a lattice of states
+uint64_t host_model_check_unscale(uint32_t stride)
+{
+    uint64_t bad = 0;
+    for (uint32_t T = 256; T < 256 + kPacket; T += 37)
+        for (uint32_t range = 16385; range <= 65536; range += stride)
+            for (uint32_t cl = 0; cl < range; cl += 1 + range / 97) {
+                const uint32_t L = 0, V = 65536u - range, code = cl;
+                const uint32_t want = ((cl + 1u) * T - 1u) / range;
+                bad += unscale(code, L, V, T) != want;
+            }
+    return bad;
+}
+
+}  // extern "C"

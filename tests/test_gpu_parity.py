@@ -1,0 +1,240 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden
+vectors.  Bit-exact: this is integer/byte work.  Run on the B200 box: pytest -m gpu."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+import _oracle as O
+from _vectors import LARGE, SMALL, VECTORS, make_input, md5
+from gpuar_b200 import datagen as D
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def codec():
+    from gpuar_b200 import codec as cd
+    cd.init()
+    return cd
+
+
+@pytest.fixture(scope="module")
+def dev(codec):
+    return codec.DeviceCodec()
+
+
+def to_dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def dev_encode(dev, data):
+    x = to_dev(data) if data.size else torch.empty(0, dtype=torch.uint8, device="cuda")
+    return dev.encode_bytes(x).cpu().numpy()
+
+
+# ------------------------------------------------------------------ encode
+@pytest.mark.parametrize("name", SMALL)
+def test_encode_equals_reference_golden(dev, name):
+    rec = VECTORS[name]
+    data = make_input(rec)
+    pay = dev_encode(dev, data)
+    assert pay.size == rec["payload_bytes"]
+    assert md5(pay) == rec["payload_md5"]
+    assert np.array_equal(pay, O.encode(data))
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 17, 31, 32, 33, 255, 4095, 8191, 8192, 8193, 8192 * 32,
+                               8192 * 32 + 1, 8192 * 33 - 1, 8192 * 64 + 77, 8192 * 97 + 4097])
+def test_encode_ragged_sizes(dev, n):
+    for data in (D.uniform(n, n), D.and3(n + 3, n)):
+        assert np.array_equal(dev_encode(dev, data), O.encode(data))
+
+
+def test_encode_empty(dev, codec):
+    assert dev_encode(dev, np.zeros(0, np.uint8)).size == 0
+    g = codec.compress(np.zeros(0, np.uint8))
+    assert g.size == 20 and O.masked_equal(g, O.gip_file(np.zeros(0, np.uint8)))
+
+
+def test_encode_packet_sizes_output(dev):
+    data = D.mixed(9, 98304)
+    x = to_dev(data)
+    sizes = torch.zeros(12, dtype=torch.int32, device="cuda")
+    payload, total, _ = dev.encode(x, sizes=sizes)
+    offs = O.index(O.encode(data))
+    want = np.diff(np.append(offs, int(total.item()))).astype(np.int32)
+    assert np.array_equal(sizes.cpu().numpy(), want)
+
+
+def test_encode_long_underflow_runs(dev):
+    rng = np.random.default_rng(5)
+    data = rng.choice(np.array([127, 128], np.uint8), size=8192 * 40, p=[0.5, 0.5])
+    assert np.array_equal(dev_encode(dev, data), O.encode(data))
+
+
+# ------------------------------------------------------------------ index
+@pytest.mark.parametrize("name", SMALL)
+def test_index_equals_chain_walk(dev, name):
+    data = make_input(VECTORS[name])
+    pay = O.encode(data)
+    c = pay.size
+    padded = torch.zeros(c + 80, dtype=torch.uint8, device="cuda")
+    padded[:c] = to_dev(pay)
+    offsets, result = dev.index(padded, c, c // 5 + 1)
+    packets, raw, status, _ = (int(v) for v in result.tolist())
+    want = O.index(pay)
+    assert status == 0 and packets == want.size and raw == data.size
+    assert np.array_equal(offsets[:packets].cpu().numpy().astype(np.uint64), want)
+
+
+def test_index_rejects_broken_chain(dev):
+    pay = O.encode(D.uniform(3, 8192 * 5)).copy()
+    pay[0] ^= 0x10                                   # first compLen now points into the middle of a packet
+    c = pay.size
+    padded = torch.zeros(c + 80, dtype=torch.uint8, device="cuda")
+    padded[:c] = to_dev(pay)
+    _, result = dev.index(padded, c, c // 5 + 1)
+    assert int(result[2].item()) != 0
+
+
+def test_index_small_packets_many_candidates(dev):
+    # all-zero input: 210-byte packets, every one a candidate, ~40 per 8 KiB of payload
+    data = D.zeros(8192 * 300)
+    pay = O.encode(data)
+    got = dev.decode_bytes(to_dev(pay)).cpu().numpy()
+    assert np.array_equal(got, data)
+
+
+# ------------------------------------------------------------------ decode
+@pytest.mark.parametrize("name", SMALL)
+def test_decode_reference_payload(dev, name):
+    data = make_input(VECTORS[name])
+    pay = O.encode(data)                             # produced by the CPU oracle, not by our encoder
+    got = dev.decode_bytes(to_dev(pay)).cpu().numpy()
+    assert np.array_equal(got, data)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 17, 8191, 8193, 8192 * 33 - 1, 8192 * 64 + 77])
+def test_decode_ragged_sizes(dev, n):
+    data = D.and3(n, n)
+    got = dev.decode_bytes(to_dev(O.encode(data))).cpu().numpy()
+    assert np.array_equal(got, data)
+
+
+# ------------------------------------------------------------ host-buffer path
+@pytest.mark.parametrize("name", ["one", "short", "maintest", "u8193", "m96k", "m1m", "u1m_tail"])
+def test_gip_image_equals_reference_under_header_mask(codec, name):
+    data = make_input(VECTORS[name])
+    g = codec.compress(data)
+    assert O.masked_equal(g, O.gip_file(data))
+    assert int.from_bytes(g[12:16].tobytes(), "little") == g.size
+    assert np.array_equal(codec.decompress(g), data)
+    # and a reference-style image (garbage in the undefined header bytes) decodes too
+    h = O.gip_file(data)
+    for k in O.HEADER_MASKED:
+        h[k] = 0xC3
+    assert np.array_equal(codec.decompress(h, out_cap=data.size), data)
+
+
+def test_host_path_multi_chunk(codec):
+    # > 3 chunks of 2048 packets: exercises the rotating staging lanes of compress_host
+    n = 8192 * 2048 * 4 + 12345
+    data = D.mixed(21, n)
+    g = codec.compress(data)
+    ref = O.ref_encode(data, threads=8) if O.have_ref() else O.encode(data)
+    assert np.array_equal(g[20:], ref)
+    assert np.array_equal(codec.decompress(g), data)
+
+
+def test_decompress_rejects_bad_magic(codec):
+    from gpuar_b200._lib import GpuarError
+    g = codec.compress(D.uniform(1, 9000)).copy()
+    g[1] = 9
+    with pytest.raises(GpuarError):
+        codec.decompress(g, out_cap=9000)
+
+
+# ------------------------------------------------------- reference-named shims
+def test_shims_use_reference_slot_layout(codec):
+    from gpuar_b200._lib import lib
+    n = 8192 * 37 + 100
+    data = D.uniform(77, n)
+    packets = O.n_packets(n)
+    src = torch.zeros(packets * 8192, dtype=torch.uint8, device="cuda")
+    src[:n] = to_dev(data)
+    slots = torch.zeros(packets * 8704, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    lib().initConstantRange()
+    lib().garCompressExecutor(src.data_ptr(), n, slots.data_ptr(), 0)
+    torch.cuda.synchronize()
+    s = slots.cpu().numpy().reshape(packets, 8704)
+    pay = O.encode(data)
+    offs = O.index(pay)
+    for p, o in enumerate(offs):
+        ln = int(s[p, 0]) | (int(s[p, 1]) << 8)
+        assert np.array_equal(s[p, :ln], pay[int(o): int(o) + ln])
+    out = torch.zeros(packets * 8192, dtype=torch.uint8, device="cuda")
+    lib().garDecompressExecutor(slots.data_ptr(), packets * 8704, out.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(out[:n].cpu().numpy(), data)
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_slots_equal_reference_gpu_kernel(codec):
+    """The reference's own garCompress kernel (compiled from its sources for sm_100) on the same device."""
+    from gpuar_b200._lib import lib
+    n = 8192 * 64
+    data = D.mixed(5, n)
+    src = to_dev(data)
+    ours = torch.zeros(64 * 8704, dtype=torch.uint8, device="cuda")
+    theirs = torch.zeros(64 * 8704, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    O.ref().gpuar_ref_gpu_init()
+    O.ref().gpuar_ref_gpu_encode(src.data_ptr(), n, theirs.data_ptr())
+    assert O.ref().gpuar_ref_gpu_sync() == 0
+    lib().garCompressExecutor(src.data_ptr(), n, ours.data_ptr(), 0)
+    torch.cuda.synchronize()
+    a, b = ours.cpu().numpy().reshape(64, 8704), theirs.cpu().numpy().reshape(64, 8704)
+    for p in range(64):
+        ln = int(b[p, 0]) | (int(b[p, 1]) << 8)
+        assert np.array_equal(a[p, :ln], b[p, :ln])
+    back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    O.ref().gpuar_ref_gpu_decode(ours.data_ptr(), 64, back.data_ptr())
+    assert O.ref().gpuar_ref_gpu_sync() == 0
+    assert np.array_equal(back.cpu().numpy(), data)
+
+
+# ------------------------------------------------------------ full-size cases
+@pytest.mark.parametrize("name", LARGE)
+def test_config2_64mib_md5(dev, name):
+    """BASELINE config 2: 64 MiB uniform random, payload byte-identical to the reference (md5), md5 round trip."""
+    rec = VECTORS[name]
+    x = D.uniform_device(rec["seed"], rec["n"])
+    assert hashlib.md5(x.cpu().numpy().tobytes()).hexdigest() == rec["input_md5"]
+    pay = dev.encode_bytes(x)
+    assert pay.numel() == rec["payload_bytes"]
+    assert hashlib.md5(pay.cpu().numpy().tobytes()).hexdigest() == rec["payload_md5"]
+    back = dev.decode_bytes(pay)
+    assert torch.equal(back, x)
+
+
+def test_config3_1gib_skewed_round_trip(dev):
+    """BASELINE config 3: 1 GiB and3 (low entropy).  Size-independent properties: round trip, ratio,
+    and prefix consistency (the first 1 MiB encodes to the golden s1m payload)."""
+    n = 1 << 30
+    x = D.and3_device(2, n)
+    payload, total, _ = dev.encode(x)
+    c = int(total.item())
+    assert 0.55 < c / n < 0.57
+    rec = VECTORS["s1m"]
+    head = payload[: rec["payload_bytes"]].cpu().numpy()
+    assert md5(head) == rec["payload_md5"]            # packets are independent: a prefix is a prefix
+    packets = n // 8192
+    offsets, result = dev.index(payload, c, packets)
+    assert [int(v) for v in result.tolist()[:3]] == [packets, n, 0]
+    back = dev.decode(payload, c, offsets, packets)
+    assert torch.equal(back, x)

@@ -1,0 +1,88 @@
+"""Closed forms used by the CUDA kernels (gpuar_b200/csrc/coder_math.h), compiled for the
+host and driven through a lane-by-lane emulation of the kernels' data flow
+(tests/host_model.cpp), against the oracle and the reference's golden vectors.  CPU only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import _oracle as O
+from _vectors import SMALL, VECTORS, make_input, md5
+from gpuar_b200 import datagen as D
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_build", "libhost_model.so")
+
+
+@pytest.fixture(scope="module")
+def model():
+    src = os.path.join(HERE, "host_model.cpp")
+    hdr = os.path.join(HERE, "..", "gpuar_b200", "csrc", "coder_math.h")
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        os.makedirs(os.path.dirname(SO), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", src, "-o", SO])
+    lib = C.CDLL(SO)
+    lib.host_model_encode_stream.restype = C.c_size_t
+    lib.host_model_encode_stream.argtypes = [O._u8p, C.c_size_t, O._u8p]
+    lib.host_model_decode_packet.restype = C.c_uint32
+    lib.host_model_decode_packet.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p]
+    lib.host_model_check_division.restype = C.c_uint64
+    lib.host_model_check_division.argtypes = [C.c_uint32]
+    lib.host_model_check_unscale.restype = C.c_uint64
+    lib.host_model_check_unscale.argtypes = [C.c_uint32]
+    return lib
+
+
+def model_encode(lib, data):
+    buf = np.zeros(O.n_packets(data.size) * O.SLOT + 64, np.uint8)
+    src = data if data.size else np.zeros(1, np.uint8)
+    return buf[: lib.host_model_encode_stream(O._ptr(src), data.size, O._ptr(buf))].copy()
+
+
+def model_decode(lib, pay, n):
+    c = pay.size
+    padded = np.zeros((c + 64 + 15) // 16 * 16, np.uint8)
+    padded[:c] = pay
+    out = np.zeros(n + O.PACKET, np.uint8)
+    pos = 0
+    for o in O.index(pay):
+        pos += lib.host_model_decode_packet(O._ptr(padded), c + 64, int(o), out[pos:].ctypes.data_as(O._u8p))
+    return out[:pos]
+
+
+def test_reciprocal_division_is_exact(model):
+    # floor(n / T) for every total T = 256..8447 around every multiple of T up to the largest numerator
+    assert model.host_model_check_division(8448 * 65536) == 0
+
+
+def test_float_estimated_divide_is_exact(model):
+    assert model.host_model_check_unscale(13) == 0
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_kernel_math_matches_reference_golden(model, name):
+    rec = VECTORS[name]
+    data = make_input(rec)
+    pay = model_encode(model, data)
+    assert pay.size == rec["payload_bytes"] and md5(pay) == rec["payload_md5"]
+    assert np.array_equal(model_decode(model, pay, data.size), data)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 63, 64, 65, 4095, 8191, 8192])
+def test_kernel_math_ragged_lengths(model, n):
+    for data in (D.uniform(n, n), D.and3(n + 1, n), D.zeros(n), D.round_robin(n)):
+        pay = model_encode(model, data)
+        assert np.array_equal(pay, O.encode(data))
+        assert np.array_equal(model_decode(model, pay, n), data)
+
+
+def test_kernel_math_long_underflow_runs(model):
+    # two-symbol inputs straddling the midpoint keep the coder in the 01../10.. state
+    rng = np.random.default_rng(5)
+    for _ in range(8):
+        data = rng.choice(np.array([127, 128], np.uint8), size=8192, p=[0.5, 0.5])
+        pay = model_encode(model, data)
+        assert np.array_equal(pay, O.encode(data))
+        assert np.array_equal(model_decode(model, pay, 8192), data)
