@@ -51,11 +51,15 @@ GPUAR_HD uint32_t bswap32(uint32_t x)
 
 // Division by the running total T = 256 + i (gpuar_kernel.cu:273,280) is a division by
 // a warp-uniform constant: floor(n / T) = mulhi(n, m) >> sh for every n < 2^30, with
-//   sh = ceil(log2 T) - 2,   m = ceil(2^(32+sh) / T) < 2^31.
-// (e = m*T - 2^(32+sh) < T, and n*e < 2^30 * 2^(sh+2) = 2^(32+sh), so the floor is exact.)
+//   sh = floor(log2 T) - 1,   m = ceil(2^(32+sh) / T) <= 2^31.
+// (e = m*T - 2^(32+sh) < T <= 2^(sh+2), and n*e < 2^30 * 2^(sh+2) = 2^(32+sh), so the floor
+// is exact; for T a power of two e = 0.)  sh only changes where T crosses a power of two,
+// i.e. at i = 256, 768, 1792, 3840, 7936 -- all multiples of 32, so it is constant over
+// any aligned run of 32 positions.
+GPUAR_HD uint32_t shift_for(uint32_t T) { return 30u - clz32(T); }
 GPUAR_HD uint32_t magic_for(uint32_t T, uint32_t &sh)
 {
-    sh = 30u - clz32(T - 1u);                        // ceil(log2 T) - 2 for T >= 256
+    sh = shift_for(T);
     const uint64_t two_p = 1ull << (32u + sh);
     return (uint32_t)((two_p + T - 1u) / T);
 }
@@ -83,26 +87,6 @@ GPUAR_HD void narrow_renorm(uint32_t &L, uint32_t &V, uint32_t lo, uint32_t hi, 
     V = (V1 << t) & 0x7FFFu;
 }
 
-// ---- encoder model pass: exclusive prefix of 8 consecutive u16 counts held as 4 packed
-// u16x2 words (c[0] = c0 | c1 << 16, ...).  Sums stay below 2^16 (<= 8448), so the packed
-// adds never carry across halves.  e[] receives the lane-local exclusive prefixes in the
-// same packing; the caller adds the warp-level base (replicated in both halves).
-GPUAR_HD uint32_t prefix8_packed(const uint32_t c[4], uint32_t e[4])
-{
-    const uint32_t a0 = c[0] * 0x10001u;             // (c0, c0+c1)
-    const uint32_t a1 = c[1] * 0x10001u;
-    const uint32_t a2 = c[2] * 0x10001u;
-    const uint32_t a3 = c[3] * 0x10001u;
-    const uint32_t s0 = a0 >> 16;                    // c0+c1
-    const uint32_t s1 = s0 + (a1 >> 16);             // c0..c3
-    const uint32_t s2 = s1 + (a2 >> 16);             // c0..c5
-    e[0] = a0 - c[0];
-    e[1] = a1 - c[1] + s0 * 0x10001u;
-    e[2] = a2 - c[2] + s1 * 0x10001u;
-    e[3] = a3 - c[3] + s2 * 0x10001u;
-    return s2 + (a3 >> 16);                          // c0..c7
-}
-
 // ---- encoder bit sink: MSB-first stream (gpuar_kernel.cu:128-151), flushed as 32-bit words
 struct BitSink {
     uint64_t acc;
@@ -120,33 +104,44 @@ struct BitSink {
             ++wp;
         }
     }
-    GPUAR_HD void put_run(uint32_t bit, uint32_t n)  // n copies of bit
-    {
-        const uint32_t ones = bit ? 0xFFFFu : 0u;
-        while (n > 16u) { put(ones, 16u); n -= 16u; }
-        put(ones & ((1u << n) - 1u), n);
-    }
 };
+
+// n copies of `bit`, any n (the rare long-underflow path and the end-of-packet flush)
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+static inline
+#endif
+BitSink put_run(BitSink out, uint32_t bit, uint32_t n)    // by value: keeps the sink in registers
+{
+    const uint32_t ones = bit ? 0xFFFFu : 0u;
+    while (n > 16u) { out.put(ones, 16u); n -= 16u; }
+    out.put(ones & ((1u << n) - 1u), n);
+    return out;
+}
 
 // Bits of one symbol: the top k bits of U1 with, right after the first of them, `pend`
 // inverted copies of it (gpuar_kernel.cu:325-336); then the underflow count carries on.
+// Common case (pend <= 16): one field of k + pend <= 32 bits, no branches.
 GPUAR_HD void emit_symbol(BitSink &out, uint32_t &pend, uint32_t k, uint32_t u, uint32_t U1)
 {
-    if (k) {
-        const uint32_t b = U1 >> 15;
-        const uint32_t rest = (U1 >> (16u - k)) & ((1u << (k - 1u)) - 1u);
-        if (pend <= 16u) {
-            const uint32_t head = (1u << pend) - (b ^ 1u);          // b, then pend x !b
-            out.put((head << (k - 1u)) | rest, k + pend);
-        } else {
-            out.put(b, 1u);
-            out.put_run(b ^ 1u, pend);
-            out.put(rest, k - 1u);
-        }
-        pend = u;
+    const uint32_t b = U1 >> 15;
+    const uint32_t km1 = k ? k - 1u : 0u;
+    const uint32_t rest = (U1 >> (16u - k)) & ((1u << km1) - 1u);
+    uint32_t val, len;
+    if (k && pend > 16u) {                                         // rare: emit b and the run first
+        out.put(b, 1u);
+        out = put_run(out, b ^ 1u, pend);
+        val = rest;
+        len = km1;
     } else {
-        pend += u;
+        const uint32_t head = (1u << (pend & 31u)) - (b ^ 1u);    // b, then pend x !b
+        val = (head << km1) | rest;
+        len = k ? k + pend : 0u;
+        val = k ? val : 0u;
     }
+    out.put(val, len);
+    pend = k ? u : pend + u;
 }
 
 // End of packet: bit 14 of L, then pend+1 inverted copies (gpuar_kernel.cu:379-388); zero
@@ -157,7 +152,7 @@ GPUAR_HD uint32_t finish_packet(BitSink &out, uint32_t L, uint32_t pend, uint8_t
     uint32_t *const first = reinterpret_cast<uint32_t *>(slot + kHdr);
     const uint32_t b = (L >> 14) & 1u;
     out.put(b, 1u);
-    out.put_run(b ^ 1u, pend + 1u);
+    out = put_run(out, b ^ 1u, pend + 1u);
     uint32_t bytes = (uint32_t)(out.wp - first) * 4u;
     if (out.nb) {
         const uint32_t tail = (out.nb + 7u) >> 3;
@@ -173,14 +168,16 @@ GPUAR_HD uint32_t finish_packet(BitSink &out, uint32_t L, uint32_t pend, uint8_t
 }
 
 // ---- decoder: target = ((code - L + 1) * T - 1) / range  (getUnscaledCode, :703-716)
-// num < 2^30 and 2^14 < range <= 2^16: a float estimate is within 1 of the quotient, one
-// correction step makes it exact.
+// num < 2^30 and 2^14 < range <= 2^16: a float estimate (approximate reciprocal, a few ulp)
+// is within 1 of the quotient; one correction step makes it exact.
 GPUAR_HD uint32_t unscale(uint32_t code, uint32_t L, uint32_t V, uint32_t T)
 {
     const uint32_t range = 65536u - V - L;
     const uint32_t num = (((code - L) & 0xFFFFu) + 1u) * T - 1u;
 #if defined(__CUDA_ARCH__)
-    uint32_t q = (uint32_t)__fmul_rz(__uint2float_rn(num), __frcp_rn(__uint2float_rn(range)));
+    float rcp;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(__uint2float_rz(range)));
+    uint32_t q = (uint32_t)(__uint2float_rz(num) * rcp);
 #else
     uint32_t q = (uint32_t)((double)(float)num * (double)(1.0f / (float)range));
 #endif
@@ -190,49 +187,120 @@ GPUAR_HD uint32_t unscale(uint32_t code, uint32_t L, uint32_t V, uint32_t T)
     return q;
 }
 
-// ---- decoder model: 4-ary cumulative-count tree, 85 nodes of three u16 thresholds
-//   t0 = |child0|, t1 = t0 + |child1|, t2 = t1 + |child2|; node n lives at base[n * stride]
-struct TreeNode { uint32_t x, y; };                   // x = t0 | t1 << 16, y = t2
-constexpr uint32_t kTreeNodes = 1 + 4 + 16 + 64;
-
-GPUAR_HD void tree_init(TreeNode *base, uint32_t stride)
+// byte permute of the 8 bytes {b:a} (prmt.b32, default mode; selector nibbles 0..7)
+GPUAR_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
-    uint32_t node = 0;
-    for (uint32_t lvl = 0, span = 64; lvl < 4; ++lvl, span >>= 2)
-        for (uint32_t q = 0; q < (1u << (2u * lvl)); ++q, ++node) {
-            base[node * stride].x = span | ((2u * span) << 16);
-            base[node * stride].y = 3u * span;
-        }
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) r |= (uint32_t)((v >> (8 * ((sel >> (4 * k)) & 7u))) & 0xFFu) << (8 * k);
+    return r;
+#endif
+}
+
+// ---- decoder model: 4-ary cumulative-count tree over the 256 symbols, 85 nodes.
+// A node is four u16 slots in one 64-bit word: (0, t0, t1, t2) with t0 = |child0|,
+// t1 = t0 + |child1|, t2 = t1 + |child2|.  Slot 0 is the constant 0 so that "the running
+// sum just below child c" is simply slot c.  Levels: 1, 4, 16, 64 nodes whose children span
+// 64, 16, 4, 1 symbols.  The root lives in registers; node n >= 1 at nodes[(n - 1) * stride].
+constexpr uint32_t kTreeNodes = 1 + 4 + 16 + 64;
+constexpr uint32_t kTreeStored = kTreeNodes - 1;
+
+GPUAR_HD uint64_t tree_node_init(uint32_t span)    // every symbol count 1
+{
+    return ((uint64_t)span << 16) | ((uint64_t)(2u * span) << 32) | ((uint64_t)(3u * span) << 48);
+}
+
+GPUAR_HD void tree_init(uint64_t &root, uint64_t *nodes, uint32_t stride)
+{
+    root = tree_node_init(64);
+    uint32_t n = 0;
+    for (uint32_t q = 0; q < 4; ++q, ++n) nodes[n * stride] = tree_node_init(16);
+    for (uint32_t q = 0; q < 16; ++q, ++n) nodes[n * stride] = tree_node_init(4);
+    for (uint32_t q = 0; q < 64; ++q, ++n) nodes[n * stride] = tree_node_init(1);
+}
+
+// One level, branch free.  rem = target relative to the node (0 <= rem < node total),
+// room = node total - rem.  All three thresholds are compared at once: with the guard
+// bit 0x8000 in every 16-bit slot, slot j of  (rem,rem,rem,rem) + guards - node  is
+// 0x8000 + rem - slot_j, whose bit 15 says rem >= slot_j, and whose low bits are already
+// the child-relative remainder.  Returns the child index c and bumps the node.
+GPUAR_HD uint32_t tree_level(uint64_t &node, uint32_t &rem, uint32_t &room)
+{
+    const uint32_t lo = (uint32_t)node, hi = (uint32_t)(node >> 32);
+    const uint32_t rr = rem * 0x10001u + 0x80008000u;
+    const uint32_t dlo = rr - lo, dhi = rr - hi;
+    const uint32_t c = (dlo >> 31) + ((dhi >> 15) & 1u) + (dhi >> 31);
+    const uint32_t p = prmt(dlo, dhi, 0x3210u + 0x2222u * c);     // slot c | slot c+1 << 16
+    rem = p & 0x7FFFu;
+    room = c == 3u ? room : 0x8000u - (p >> 16);
+    node += 0x0001000100010000ull << (16u * c);                    // +1 on every slot above c
+    return c;
 }
 
 // Finds the symbol whose cumulative interval holds `target` (getSymbolFromProbability,
 // :727-763), returns it with lo = cum[s], cnt = count[s], and bumps count[s] (:288).
-GPUAR_HD uint32_t tree_decode(TreeNode *base, uint32_t stride, uint32_t target, uint32_t total, uint32_t &lo,
-                              uint32_t &cnt)
+GPUAR_HD uint32_t tree_decode(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t target, uint32_t total,
+                              uint32_t &lo, uint32_t &cnt)
 {
-    uint32_t rem = target, tot = total, idx = 0, acc = 0, first = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (uint32_t lvl = 0; lvl < 4; ++lvl) {
-        TreeNode *n = base + (first + idx) * stride;
-        TreeNode t = *n;
-        const uint32_t t0 = t.x & 0xFFFFu, t1 = t.x >> 16, t2 = t.y;
-        const uint32_t c = (uint32_t)(rem >= t0) + (uint32_t)(rem >= t1) + (uint32_t)(rem >= t2);
-        const uint32_t below = c == 0 ? 0u : c == 1 ? t0 : c == 2 ? t1 : t2;
-        const uint32_t above = c == 0 ? t0 : c == 1 ? t1 : c == 2 ? t2 : tot;
-        t.x += c == 0 ? 0x00010001u : c == 1 ? 0x00010000u : 0u;
-        t.y += c <= 2 ? 1u : 0u;
-        *n = t;
-        rem -= below;
-        acc += below;
-        tot = above - below;
-        idx = idx * 4u + c;
-        first += 1u << (2u * lvl);
+    uint32_t rem = target, room = total - target;
+    uint32_t idx = tree_level(root, rem, room);
+    {
+        uint64_t *n = nodes + idx * stride;
+        uint64_t v = *n;
+        idx = idx * 4u + tree_level(v, rem, room);
+        *n = v;
     }
+    {
+        uint64_t *n = nodes + (4u + idx) * stride;
+        uint64_t v = *n;
+        idx = idx * 4u + tree_level(v, rem, room);
+        *n = v;
+    }
+    {
+        uint64_t *n = nodes + (20u + idx) * stride;
+        uint64_t v = *n;
+        idx = idx * 4u + tree_level(v, rem, room);
+        *n = v;
+    }
+    lo = target - rem;
+    cnt = rem + room;
+    return idx;
+}
+
+// Encoder side of the same model: the symbol is known, so the four child indices are its
+// bit pairs and the four node loads are independent of each other.  Returns lo = cum[s],
+// cnt = count[s] as they were before this symbol, and bumps count[s]
+// (getRange(LOWER/UPPER) + update, gpuar_kernel.cu:215-238,272,279,288).
+GPUAR_HD void tree_step_known(uint64_t &node, uint32_t c, uint32_t &lo, uint32_t &tot)
+{
+    const uint32_t p = prmt((uint32_t)node, (uint32_t)(node >> 32), 0x3210u + 0x2222u * c);  // slot c | slot c+1 << 16
+    const uint32_t below = p & 0xFFFFu;
+    const uint32_t above = c == 3u ? tot : (p >> 16);
+    lo += below;
+    tot = above - below;
+    node += 0x0001000100010000ull << (16u * c);
+}
+
+GPUAR_HD void tree_encode(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t s, uint32_t total,
+                          uint32_t &lo, uint32_t &cnt)
+{
+    uint64_t *const p1 = nodes + (s >> 6) * stride;
+    uint64_t *const p2 = nodes + (4u + (s >> 4)) * stride;
+    uint64_t *const p3 = nodes + (20u + (s >> 2)) * stride;
+    uint64_t n1 = *p1, n2 = *p2, n3 = *p3;
+    uint32_t acc = 0, tot = total;
+    tree_step_known(root, s >> 6, acc, tot);
+    tree_step_known(n1, (s >> 4) & 3u, acc, tot);
+    tree_step_known(n2, (s >> 2) & 3u, acc, tot);
+    tree_step_known(n3, s & 3u, acc, tot);
+    *p1 = n1;
+    *p2 = n2;
+    *p3 = n3;
     lo = acc;
     cnt = tot;
-    return idx;
 }
 
 // ---- decoder bit source: 64-bit reservoir, next bit = MSB, fed one 32-bit word at a time

@@ -8,13 +8,13 @@
 //
 // Here the adaptive model of each packet is a 4-ary cumulative-count tree in shared
 // memory, interleaved so that lane l only ever touches bank pair (2l, 2l+1):
-//   level 0: 1 node  (children span 64 symbols)      node = 3 running thresholds
+//   level 0: 1 node  (children span 64 symbols)      node = four u16 slots (0, t0, t1, t2):
 //   level 1: 4 nodes (16)                            t0 = |child0|, t1 = t0+|child1|,
-//   level 2: 16 nodes (4)                            t2 = t1+|child2|   (u16 each)
+//   level 2: 16 nodes (4)                            t2 = t1+|child2|
 //   level 3: 64 nodes (1)
-// One descent (4 dependent 8-byte loads) finds the symbol, yields cum[s] and count[s]
-// and applies the model update (+1 on every threshold at or right of the path) in the
-// same pass.  Interval arithmetic and renormalisation are the closed forms of
+// One branch-free descent (root in registers, then 3 dependent 8-byte shared loads) finds
+// the symbol, yields cum[s] and count[s] and applies the model update (+1 on every slot
+// right of the path) in the same pass (coder_math.h: tree_level).  Interval arithmetic and renormalisation are the closed forms of
 // common.cuh; bits come from a 64-bit reservoir fed by 32-bit loads one word ahead.
 #include "common.cuh"
 #include "kernels.h"
@@ -27,7 +27,7 @@ __device__ __forceinline__ const uint32_t *clamp_ptr(const uint32_t *p, const ui
 }
 
 struct DecShared {
-    TreeNode tree[kTreeNodes][32];   // 21760 B; lane l owns column l (banks 2l, 2l+1)
+    uint64_t tree[kTreeStored][32];  // 21504 B; lane l owns column l (banks 2l, 2l+1); root in registers
 };
 
 __global__ void __launch_bounds__(32)
@@ -40,13 +40,15 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     const bool mine = my < n_packets;
 
     // model init: every count 1 (gpuar_kernel.cu:403-419)
-    TreeNode *const tree = &sm.tree[0][lane];
-    tree_init(tree, 32u);
+    uint64_t *const tree = &sm.tree[0][lane];
+    uint64_t root;
+    tree_init(root, tree, 32u);
 
     // bit source: aligned 32-bit words of the packet's bitstream, one word prefetched
     const uint32_t *const wend = reinterpret_cast<const uint32_t *>(payload) + (readable >> 2) - 1;  // last readable word
     const uint32_t *wp = wend;      // word held in `ahead`
-    uint32_t ahead = 0;             // prefetched word, big-endian (first stream bit = MSB)
+    uint32_t ahead = 0;             // prefetched word, still little-endian: swapped when fed, so that
+                                    // nothing waits on the load until the reservoir needs it
     BitSource in;
     in.buf = 0;
     in.have = 64u;
@@ -63,14 +65,14 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
         ++wp;
         in.feed(bswap32(*clamp_ptr(wp, wend)));                          // 40..64 bits
         ++wp;
-        ahead = bswap32(*clamp_ptr(wp, wend));
+        ahead = *clamp_ptr(wp, wend);
     }
     // initializeDecoder (:582-603): the first 16 bits
     uint32_t code = in.take(16u);
     if (in.hungry()) {
-        in.feed(ahead);
+        in.feed(bswap32(ahead));
         ++wp;
-        ahead = bswap32(*clamp_ptr(wp, wend));
+        ahead = *clamp_ptr(wp, wend);
     }
     uint32_t L = 0, V = 0;
 
@@ -78,41 +80,57 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)my * kPacket);
     uint32_t packed = 0;
 
+    // one symbol of this lane's packet; `slot` = position of the byte inside the 32-bit store word
+    auto step = [&](uint32_t i, uint32_t m, uint32_t sh, uint32_t slot) {
+        const uint32_t T = 256u + i;
+        const uint32_t target = unscale(code, L, V, T);
+        uint32_t lo, cnt;
+        const uint32_t s = tree_decode(root, tree, 32u, target, T, lo, cnt);
+        packed |= s << (8u * slot);
+        uint32_t k, u, U1;
+        narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
+        code = advance_code(code, k, u, in);
+        if (in.hungry()) {
+            in.feed(bswap32(ahead));
+            ++wp;
+            ahead = *clamp_ptr(wp, wend);
+        }
+    };
+
+    const uint32_t min_raw = __reduce_min_sync(kFull, mine ? raw : kPacket);
     const uint32_t rounds = (max_raw + 31u) >> 5;
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t i0 = r * 32u;
-        uint32_t sh_l;
-        const uint32_t m_l = magic_for(256u + i0 + lane, sh_l);    // lane j holds the divisor of step j
+        uint32_t sh;
+        const uint32_t m_l = magic_for(256u + i0 + lane, sh);      // lane j holds the multiplier of step j
+        sh = shift_for(256u + i0);                                 // the shift is uniform over the round
+        if (i0 + 32u <= min_raw) {
+            // every lane of the warp has all 32 positions: no per-lane predicates
 #pragma unroll 4
-        for (uint32_t j = 0; j < 32u; ++j) {
-            const uint32_t m = __shfl_sync(kFull, m_l, j);
-            const uint32_t sh = __shfl_sync(kFull, sh_l, j);
-            const uint32_t i = i0 + j;
-            if (i < raw) {
-                const uint32_t T = 256u + i;
-                const uint32_t target = unscale(code, L, V, T);
-                uint32_t lo, cnt;
-                const uint32_t s = tree_decode(tree, 32u, target, T, lo, cnt);
-                packed |= s << (8u * (j & 3u));
-                uint32_t k, u, U1;
-                narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
-                code = advance_code(code, k, u, in);
-                if (in.hungry()) {
-                    in.feed(ahead);
-                    ++wp;
-                    ahead = bswap32(*clamp_ptr(wp, wend));
+            for (uint32_t j = 0; j < 32u; ++j) {
+                step(i0 + j, __shfl_sync(kFull, m_l, j), sh, j & 3u);
+                if ((j & 3u) == 3u) {
+                    if (mine) dst[(i0 + j) >> 2] = packed;
+                    packed = 0;
                 }
             }
-            if ((j & 3u) == 3u) {
-                if (mine && (i & ~3u) < raw) {
-                    if (i < raw) {
-                        dst[i >> 2] = packed;
-                    } else {                                       // ragged tail of the last packet
-                        uint8_t *b = reinterpret_cast<uint8_t *>(dst) + (i & ~3u);
-                        for (uint32_t q = 0; q < (raw & 3u); ++q) b[q] = (uint8_t)(packed >> (8u * q));
+        } else {
+            // ragged tail (only the warp holding the last packet of the stream gets here)
+            for (uint32_t j = 0; j < 32u; ++j) {
+                const uint32_t m = __shfl_sync(kFull, m_l, j);
+                const uint32_t i = i0 + j;
+                if (i < raw) step(i, m, sh, j & 3u);
+                if ((j & 3u) == 3u) {
+                    if (mine && (i & ~3u) < raw) {
+                        if (i < raw) {
+                            dst[i >> 2] = packed;
+                        } else {
+                            uint8_t *b = reinterpret_cast<uint8_t *>(dst) + (i & ~3u);
+                            for (uint32_t q = 0; q < (raw & 3u); ++q) b[q] = (uint8_t)(packed >> (8u * q));
+                        }
                     }
+                    packed = 0;
                 }
-                packed = 0;
             }
         }
     }

@@ -1,26 +1,23 @@
-// encode.cu -- sm_100a encode path: model pass + coder pass (one kernel), then a
-// single-pass decoupled-look-back scan of the packet sizes fused with the
+// encode.cu -- sm_100a encode path: one fused model+coder kernel with lane = packet,
+// then a single-pass decoupled-look-back scan of the packet sizes fused with the
 // compaction of the bitstreams into the .gip payload layout.
 //
 // Replaces garCompress / arCompress (reference src/gpuar_kernel.cu:487-531,
 // 894-914) and the host-side compaction loop (src/gpu_compressor.cpp:136-169).
 //
-// Work decomposition:
-//   one warp owns 32 packets and alternates, 32 input positions at a time, between
-//   (A) MODEL PASS, warp-cooperative, one packet at a time: lane j takes symbol
-//       x[i0+j] and computes the cumulative-frequency pair the adaptive model
-//       would hand the coder at that position,
-//           lo = cum[s] = pre[s] + #{earlier symbols of this tile that are < s}
-//           cnt = count[s] + #{earlier symbols of this tile that are == s}
-//       from the running 256-bin histogram `cnt` and its exclusive scan `pre` in
-//       shared memory (ballot bit-plane ranks inside the tile, packed warp-shuffle
-//       scan to refresh `pre`).  This equals the reference's getRange() pair
-//       (gpuar_kernel.cu:215-227,272,279) without the Fenwick tree, because the
-//       model does not depend on the coder state.
-//   (B) CODER PASS, lane = packet: the serial interval recurrence
-//       (gpuar_kernel.cu:256-288, 321-367) in closed form, dividing by the
-//       warp-uniform total with a multiply; bits go to a 64-bit accumulator that is
-//       flushed as 32-bit words into the packet's slot.
+// Work decomposition: a warp owns 32 packets, lane = packet, and all lanes
+// advance through their packets in lock step (position i of 32 different packets per
+// step), so the running total T = 256 + i -- the divisor of both interval divisions -- is
+// warp-uniform and becomes a multiply by a per-step reciprocal.  Per symbol:
+//   MODEL  cum[s], count[s] and count[s]++ from the packet's 4-ary cumulative-count tree
+//          in shared memory (coder_math.h: tree_encode): root in registers, three
+//          independent 8-byte loads/stores, byte permutes instead of branches.  Equals the
+//          reference's two Fenwick prefix sums + update (gpuar_kernel.cu:215-238).
+//   CODER  the interval recurrence (gpuar_kernel.cu:256-288) and the renormalisation
+//          loop (:321-367) in closed form; bits go to a 64-bit accumulator flushed as
+//          32-bit words into the packet's slot.
+// The model does not depend on the coder state, so the model work of symbol i+1 overlaps
+// the dependent coder chain of symbol i inside each warp.
 #include "common.cuh"
 #include "kernels.h"
 #include "lookback.cuh"
@@ -29,10 +26,7 @@ namespace gpuar {
 
 // ------------------------------------------------------------------ encode
 struct EncShared {
-    uint16_t cnt[32][256];   // running symbol counts per packet (all start at 1)
-    uint16_t pre[32][256];   // exclusive scan of cnt
-    uint32_t pair[32][33];   // (lo | cnt << 16) for the 32 positions of the round, padded
-    uint32_t in[32][8];      // the round's 32 input bytes of each packet
+    uint64_t tree[kTreeStored][32];  // 21504 B; lane l owns column l (banks 2l, 2l+1); root in registers
 };
 
 __global__ void __launch_bounds__(32)
@@ -41,136 +35,77 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
 {
     __shared__ __align__(16) EncShared sm;
     const uint32_t lane = lane_id();
-    const uint32_t p0 = blockIdx.x * 32u;
-    const uint32_t ltmask = (1u << lane) - 1u;
-
-    // model init: counts 1, prefix = symbol index (gpuar_kernel.cu:403-419)
-    for (uint32_t p = 0; p < 32; ++p) {
-        uint32_t *c = reinterpret_cast<uint32_t *>(sm.cnt[p]);
-        uint32_t *q = reinterpret_cast<uint32_t *>(sm.pre[p]);
-        for (uint32_t w = lane; w < 128; w += 32) {
-            c[w] = 0x00010001u;
-            q[w] = (2u * w) | ((2u * w + 1u) << 16);
-        }
-    }
-
-    // this lane's packet (coder pass)
-    const uint32_t my = p0 + lane;
+    const uint32_t my = blockIdx.x * 32u + lane;
     const bool mine = my < n_packets;
-    uint32_t my_len = 0;
-    if (mine) {
-        const size_t off = (size_t)my * kPacket;
-        my_len = (n - off < kPacket) ? (uint32_t)(n - off) : kPacket;
-    }
-    // lengths are 8192 except possibly for the last packet of the stream
-    const uint32_t warp_packets = min(32u, n_packets - p0);
-    const uint32_t max_len = __reduce_max_sync(kFull, my_len);
+
+    uint64_t *const tree = &sm.tree[0][lane];
+    uint64_t root;
+    tree_init(root, tree, 32u);                                   // all counts 1 (:403-419)
+
+    const size_t off = (size_t)my * kPacket;
+    uint32_t len = 0;                                             // 8192 except for the last packet
+    if (mine) len = (n - off < kPacket) ? (uint32_t)(n - off) : kPacket;
+    const uint32_t max_len = __reduce_max_sync(kFull, len);
+    const uint32_t min_len = __reduce_min_sync(kFull, mine ? len : kPacket);
 
     uint32_t L = 0, V = 0, pend = 0;
+    uint8_t *const slot = slots + (size_t)my * slot_stride;
     BitSink out;
     out.acc = 0;
     out.nb = 0;
-    uint8_t *slot = slots + (size_t)my * slot_stride;
     out.wp = reinterpret_cast<uint32_t *>(slot + kHdr);
     out.end = reinterpret_cast<uint32_t *>(slot + (mine ? (slot_stride & ~3u) : 0u));
 
-    // staging: per round the warp needs 32 B from each of its packets = 64 x 16 B;
-    // lane l fetches chunks l and l+32 (packet = chunk>>1, half = chunk&1)
-    auto fetch = [&](uint32_t round, uint32_t chunk) -> uint4 {
-        const uint32_t p = chunk >> 1;
-        const size_t a = (size_t)(p0 + p) * kPacket + round * 32u + (chunk & 1u) * 16u;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        // the 16-byte read stays inside the caller's buffer rounded up to 16 (API contract)
-        if (p < warp_packets && a < n) v = *reinterpret_cast<const uint4 *>(src + a);
-        return v;
+    // 16 input bytes per lane per half round, fetched one half round ahead.  The read may
+    // run up to 15 bytes past n inside the caller's 16-byte-rounded buffer (API contract).
+    const uint4 *const in16 = reinterpret_cast<const uint4 *>(src + off);
+    auto fetch = [&](uint32_t h) -> uint4 {
+        return (h * 16u < len) ? __ldg(in16 + h) : make_uint4(0, 0, 0, 0);
     };
-    uint4 nx0 = fetch(0, lane), nx1 = fetch(0, lane + 32u);
+    uint4 ahead = fetch(0);
+
+    auto step = [&](uint32_t i, uint32_t s, uint32_t m, uint32_t sh) {
+        uint32_t lo, cnt, k, u, U1;
+        tree_encode(root, tree, 32u, s, 256u + i, lo, cnt);
+        narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
+        emit_symbol(out, pend, k, u, U1);
+    };
 
     const uint32_t rounds = (max_len + 31u) >> 5;
     for (uint32_t r = 0; r < rounds; ++r) {
-        __syncwarp();
-        *reinterpret_cast<uint4 *>(&sm.in[lane >> 1][(lane & 1u) * 4u]) = nx0;
-        *reinterpret_cast<uint4 *>(&sm.in[16u + (lane >> 1)][(lane & 1u) * 4u]) = nx1;
-        if (r + 1 < rounds) {
-            nx0 = fetch(r + 1, lane);
-            nx1 = fetch(r + 1, lane + 32u);
-        }
-        __syncwarp();
-
-        // ---------------- (A) model pass: one packet at a time, lane = position
         const uint32_t i0 = r * 32u;
-        for (uint32_t p = 0; p < warp_packets; ++p) {
-            const size_t off = (size_t)(p0 + p) * kPacket;
-            const uint32_t plen = (n - off < kPacket) ? (uint32_t)(n - off) : kPacket;
-            if (i0 >= plen) continue;                              // warp-uniform
-            const uint32_t valid = min(32u, plen - i0);
-            const bool act = lane < valid;
-            const uint32_t amask = (valid == 32u) ? kFull : ((1u << valid) - 1u);
-
-            const uint32_t s = reinterpret_cast<const uint8_t *>(sm.in[p])[lane];
-            const uint32_t c_before = sm.cnt[p][s];
-            const uint32_t p_before = sm.pre[p][s];
-
-            // ranks inside the tile from 8 bit-plane ballots (MSB first):
-            //   E  = lanes whose symbol equals mine on the planes seen so far
-            //   LT = lanes whose symbol is smaller than mine
-            uint32_t E = amask, LT = 0;
+        uint32_t sh;
+        const uint32_t m_l = magic_for(256u + i0 + lane, sh);     // lane j holds the multiplier of step j
+        sh = shift_for(256u + i0);                                // the shift is uniform over the round
+        const bool full = i0 + 32u <= min_len;                    // every lane has all 32 positions
+#pragma unroll 1
+        for (uint32_t h = 0; h < 2u; ++h) {
+            const uint4 cur = ahead;
+            ahead = fetch(2u * r + h + 1u);
+            // 4 symbols per inner iteration: the loop body stays small enough for the
+            // instruction cache (a fully unrolled round is ~60 KB of SASS)
+#pragma unroll 1
+            for (uint32_t q = 0; q < 4u; ++q) {
+                const uint32_t word = q == 0u ? cur.x : q == 1u ? cur.y : q == 2u ? cur.z : cur.w;
+                const uint32_t j0 = 16u * h + 4u * q;
+                if (full) {
 #pragma unroll
-            for (int b = 7; b >= 0; --b) {
-                const bool bit = (s >> b) & 1u;
-                const uint32_t B = __ballot_sync(kFull, bit && act);
-                if (bit) {
-                    LT |= E & ~B;
-                    E &= B;
+                    for (uint32_t j = 0; j < 4u; ++j)
+                        step(i0 + j0 + j, (word >> (8u * j)) & 0xFFu, __shfl_sync(kFull, m_l, j0 + j), sh);
                 } else {
-                    E &= ~B;
+                    // ragged tail: only the warp holding the last packet of the stream gets here
+#pragma unroll 1
+                    for (uint32_t j = 0; j < 4u; ++j) {
+                        const uint32_t m = __shfl_sync(kFull, m_l, j0 + j);
+                        if (i0 + j0 + j < len) step(i0 + j0 + j, (word >> (8u * j)) & 0xFFu, m, sh);
+                    }
                 }
-            }
-            const uint32_t lo = p_before + __popc(LT & ltmask);
-            const uint32_t c = c_before + __popc(E & ltmask);
-            sm.pair[p][lane] = lo | (c << 16);
-
-            // the last lane of each equal-symbol group adds the group to the histogram
-            if (act && (E >> lane) == 1u) sm.cnt[p][s] = (uint16_t)(c_before + __popc(E));
-            __syncwarp();
-
-            // refresh pre = exclusive scan of cnt: 8 bins per lane, packed u16x2
-            const uint4 c4 = *reinterpret_cast<const uint4 *>(&sm.cnt[p][8u * lane]);
-            const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
-            uint32_t ew[4];
-            const uint32_t tot = prefix8_packed(cw, ew);
-            uint32_t inc = tot;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(kFull, inc, d);
-                if (lane >= (uint32_t)d) inc += t;
-            }
-            const uint32_t base = (inc - tot) * 0x10001u;
-            const uint4 e = make_uint4(ew[0] + base, ew[1] + base, ew[2] + base, ew[3] + base);
-            *reinterpret_cast<uint4 *>(&sm.pre[p][8u * lane]) = e;
-        }
-        __syncwarp();
-
-        // ---------------- (B) coder pass: lane = packet, 32 positions
-        uint32_t sh_l;
-        const uint32_t m_l = magic_for(256u + i0 + lane, sh_l);    // lane j holds the divisor of step j
-        const uint32_t steps = min(32u, max_len - i0);
-        for (uint32_t j = 0; j < steps; ++j) {
-            const uint32_t m = __shfl_sync(kFull, m_l, j);
-            const uint32_t sh = __shfl_sync(kFull, sh_l, j);
-            if (i0 + j < my_len) {
-                const uint32_t pr = sm.pair[lane][j];
-                const uint32_t lo = pr & 0xFFFFu;
-                const uint32_t hi = lo + (pr >> 16);
-                uint32_t k, u, U1;
-                narrow_renorm(L, V, lo, hi, m, sh, k, u, U1);
-                emit_symbol(out, pend, k, u, U1);
             }
         }
     }
 
     if (mine) {
-        const uint32_t comp = finish_packet(out, L, pend, slot, my_len);
+        const uint32_t comp = finish_packet(out, L, pend, slot, len);
         if (sizes) sizes[my] = comp;
     }
 }

@@ -1,9 +1,9 @@
 // host_model.cpp -- CPU emulation of the CUDA kernels' data flow, built with g++ from the
 // SAME arithmetic source the kernels use (gpuar_b200/csrc/coder_math.h).  Test
 // infrastructure: it lets `pytest -m "not gpu"` check the closed forms (reciprocal
-// division, renormalisation, bit packing, packed-u16 scans, ballot ranks, the 4-ary
-// model tree, the float-estimated divide) against the oracle without a GPU.  The warp
-// is emulated lane by lane; ballots and shuffles become loops over 32 lanes.
+// division, renormalisation, bit packing, the 4-ary model tree with its packed compares
+// and byte permutes, the float-estimated divide) against the oracle without a GPU.  Both
+// kernels are lane = packet, so one lane is emulated at a time.
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -12,63 +12,14 @@
 
 using namespace gpuar;
 
-namespace {
-
-// model pass of encode_kernel for one packet: pair[i] = lo | cnt << 16
-void model_pass(const uint8_t *x, uint32_t n, std::vector<uint32_t> &pair)
-{
-    uint16_t cnt[256], pre[256];
-    for (int s = 0; s < 256; ++s) { cnt[s] = 1; pre[s] = (uint16_t)s; }
-    pair.resize(n);
-    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
-        const uint32_t valid = n - i0 < 32 ? n - i0 : 32;
-        const uint32_t amask = valid == 32 ? 0xFFFFFFFFu : ((1u << valid) - 1u);
-        uint32_t sym[32], E[32], LT[32];
-        for (uint32_t l = 0; l < 32; ++l) { sym[l] = l < valid ? x[i0 + l] : 0; E[l] = amask; LT[l] = 0; }
-        for (int b = 7; b >= 0; --b) {
-            uint32_t B = 0;                                        // __ballot_sync(bit && act)
-            for (uint32_t l = 0; l < 32; ++l) B |= (uint32_t)(((sym[l] >> b) & 1u) && l < valid) << l;
-            for (uint32_t l = 0; l < 32; ++l) {
-                if ((sym[l] >> b) & 1u) { LT[l] |= E[l] & ~B; E[l] &= B; }
-                else E[l] &= ~B;
-            }
-        }
-        uint16_t newcnt[256];
-        memcpy(newcnt, cnt, sizeof cnt);
-        for (uint32_t l = 0; l < valid; ++l) {
-            const uint32_t ltmask = (1u << l) - 1u;
-            const uint32_t lo = pre[sym[l]] + (uint32_t)__builtin_popcount(LT[l] & ltmask);
-            const uint32_t c = cnt[sym[l]] + (uint32_t)__builtin_popcount(E[l] & ltmask);
-            pair[i0 + l] = lo | (c << 16);
-            if ((E[l] >> l) == 1u) newcnt[sym[l]] = (uint16_t)(cnt[sym[l]] + __builtin_popcount(E[l]));
-        }
-        memcpy(cnt, newcnt, sizeof cnt);
-        // packed rescan: lane l owns bins 8l..8l+7
-        uint32_t tot[32], e[32][4];
-        for (uint32_t l = 0; l < 32; ++l) {
-            uint32_t c[4];
-            memcpy(c, &cnt[8 * l], 16);
-            tot[l] = prefix8_packed(c, e[l]);
-        }
-        uint32_t run = 0;
-        for (uint32_t l = 0; l < 32; ++l) {
-            const uint32_t base = run * 0x10001u;
-            uint32_t w[4] = {e[l][0] + base, e[l][1] + base, e[l][2] + base, e[l][3] + base};
-            memcpy(&pre[8 * l], w, 16);
-            run += tot[l];
-        }
-    }
-}
-
-}  // namespace
-
 extern "C" {
 
 // encode one packet exactly as a lane of encode_kernel does; returns compLen
 uint32_t host_model_encode_packet(const uint8_t *x, uint32_t n, uint8_t *slot, uint32_t slot_bytes)
 {
-    std::vector<uint32_t> pair;
-    model_pass(x, n, pair);
+    std::vector<uint64_t> tree(kTreeStored);
+    uint64_t root;
+    tree_init(root, tree.data(), 1);
     uint32_t L = 0, V = 0, pend = 0;
     BitSink out;
     out.acc = 0;
@@ -78,9 +29,9 @@ uint32_t host_model_encode_packet(const uint8_t *x, uint32_t n, uint8_t *slot, u
     for (uint32_t i = 0; i < n; ++i) {
         uint32_t sh;
         const uint32_t m = magic_for(256u + i, sh);
-        const uint32_t lo = pair[i] & 0xFFFFu, hi = lo + (pair[i] >> 16);
-        uint32_t k, u, U1;
-        narrow_renorm(L, V, lo, hi, m, sh, k, u, U1);
+        uint32_t lo, cnt, k, u, U1;
+        tree_encode(root, tree.data(), 1, x[i], 256u + i, lo, cnt);
+        narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
         emit_symbol(out, pend, k, u, U1);
     }
     return finish_packet(out, L, pend, slot, n);
@@ -103,8 +54,9 @@ size_t host_model_encode_stream(const uint8_t *in, size_t n, uint8_t *payload)
 // lane of decode_kernel does; returns bytes produced
 uint32_t host_model_decode_packet(const uint8_t *payload, size_t readable, size_t off, uint8_t *out)
 {
-    std::vector<TreeNode> tree(kTreeNodes);
-    tree_init(tree.data(), 1);
+    std::vector<uint64_t> tree(kTreeStored);
+    uint64_t root;
+    tree_init(root, tree.data(), 1);
     const uint32_t *const words = reinterpret_cast<const uint32_t *>(payload);
     const uint32_t *const wend = words + (readable >> 2) - 1;
     auto word = [&](const uint32_t *p) { return bswap32(*(p < wend ? p : wend)); };
@@ -128,7 +80,7 @@ uint32_t host_model_decode_packet(const uint8_t *payload, size_t readable, size_
         const uint32_t m = magic_for(T, sh);
         const uint32_t target = unscale(code, L, V, T);
         uint32_t lo, cnt;
-        const uint32_t s = tree_decode(tree.data(), 1, target, T, lo, cnt);
+        const uint32_t s = tree_decode(root, tree.data(), 1, target, T, lo, cnt);
         out[i] = (uint8_t)s;
         uint32_t k, u, U1;
         narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
