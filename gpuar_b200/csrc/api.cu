@@ -382,6 +382,22 @@ int gpuar_b200_peer_concat(uint8_t *d_dst, int dst_device, size_t dst_offset, co
     return ck(cudaMemcpyPeerAsync(d_dst + dst_offset, dst_device, d_src, src_device, bytes, (cudaStream_t)stream));
 }
 
+int gpuar_b200_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, int rank, int world,
+                            uint8_t *d_gather, size_t gather_cap, void *stream)
+{
+    if (!d_payload || !d_totals || !d_gather || rank < 0 || rank >= world) return GPUAR_E_ARG;
+    if ((uintptr_t)d_payload & 15u) return GPUAR_E_ARG;
+    return ck(launch_shard_concat(d_payload, d_totals, (uint32_t)rank, d_gather, gather_cap, (cudaStream_t)stream));
+}
+
+int gpuar_b200_device_alloc(size_t bytes, void **d_ptr)
+{
+    if (!d_ptr) return GPUAR_E_ARG;
+    return ck(cudaMalloc(d_ptr, bytes));
+}
+
+int gpuar_b200_device_free(void *d_ptr) { return ck(cudaFree(d_ptr)); }
+
 int gpuar_b200_ipc_export(const void *d_ptr, uint8_t handle[64])
 {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");

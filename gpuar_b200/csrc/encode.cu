@@ -198,6 +198,31 @@ compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const ui
     }
 }
 
+// ------------------------------------------------- multi-GPU stream concatenation
+// Rank r's compacted payload lands at the exclusive scan of the ranks' totals inside the
+// gathered payload, which may live on another GPU of the box: `gather` is then a
+// peer-mapped pointer (cudaIpcOpenMemHandle) and the 16-byte stores below travel over
+// NVLink.  The totals are read from device memory, so the host never waits for a size.
+constexpr uint32_t kConcatThreads = 256;
+constexpr uint32_t kConcatPiece = 4096;             // bytes per warp-iteration (16-byte aligned source)
+
+__global__ void __launch_bounds__(kConcatThreads)
+shard_concat_kernel(const uint8_t *__restrict__ payload, const uint64_t *__restrict__ totals, uint32_t rank,
+                    uint8_t *__restrict__ gather, uint64_t gather_cap)
+{
+    uint64_t base = 0;
+    for (uint32_t r = 0; r < rank; ++r) base += totals[r];
+    const uint64_t bytes = totals[rank];
+    if (base + bytes > gather_cap) return;           // never write past the destination
+    const uint32_t lane = lane_id();
+    const uint64_t warps = (uint64_t)gridDim.x * (kConcatThreads / 32u);
+    const uint64_t w = (uint64_t)blockIdx.x * (kConcatThreads / 32u) + (threadIdx.x >> 5);
+    for (uint64_t at = w * kConcatPiece; at < bytes; at += warps * kConcatPiece) {
+        const uint32_t len = (uint32_t)min((uint64_t)kConcatPiece, bytes - at);
+        warp_copy_unaligned(gather + base + at, payload + at, len, lane);
+    }
+}
+
 // ------------------------------------------------------------------ launchers
 const void *probe_kernel() { return reinterpret_cast<const void *>(&encode_kernel); }
 
@@ -228,6 +253,17 @@ cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const u
     uint32_t *ticket = reinterpret_cast<uint32_t *>(d_desc + tiles);
     compact_kernel<<<tiles, kCompactThreads, 0, st>>>(d_slots, slot_stride, d_sizes, packets, d_payload,
                                                       d_desc, ticket, d_total);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, uint32_t rank, uint8_t *d_gather,
+                                uint64_t gather_cap, cudaStream_t st)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    shard_concat_kernel<<<(unsigned)sms * 4u, kConcatThreads, 0, st>>>(d_payload, d_totals, rank, d_gather, gather_cap);
     count_launch();
     return cudaGetLastError();
 }

@@ -117,6 +117,15 @@ int gpuar_b200_check_header(const uint8_t hdr[20]);
  * cudaIpcOpenMemHandle mapping.  Asynchronous on `stream`. */
 int gpuar_b200_peer_concat(uint8_t *d_dst, int dst_device, size_t dst_offset, const uint8_t *d_src,
                            int src_device, size_t bytes, void *stream);
+/* The same without a host round trip (what bench.py --gpus N uses): one kernel per rank reads
+ * the W payload totals from device memory (d_totals[world], e.g. all-gathered), takes its
+ * exclusive scan at `rank` as the landing offset and stores d_payload[0..totals[rank]) into
+ * d_gather -- a local or peer-mapped (IPC) pointer -- with 16-byte stores over NVLink. */
+int gpuar_b200_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, int rank, int world,
+                            uint8_t *d_gather, size_t gather_cap, void *stream);
+/* plain cudaMalloc/cudaFree on the current device: IPC-exportable allocations for the gather buffer */
+int gpuar_b200_device_alloc(size_t bytes, void **d_ptr);
+int gpuar_b200_device_free(void *d_ptr);
 int gpuar_b200_ipc_export(const void *d_ptr, uint8_t handle[64]);
 int gpuar_b200_ipc_open(const uint8_t handle[64], void **d_ptr);
 int gpuar_b200_ipc_close(void *d_ptr);
