@@ -50,6 +50,10 @@ SIGNATURES = {
     "gpuar_b200_shard_concat": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _sz, _vp]),
     "gpuar_b200_device_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
     "gpuar_b200_device_free": (C.c_int, [_vp]),
+    "gpuar_b200_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
+    "gpuar_b200_host_free": (C.c_int, [_vp]),
+    "gpuar_b200_device_count": (C.c_int, []),
+    "gpuar_b200_set_device": (C.c_int, [C.c_int]),
     "gpuar_b200_ipc_export": (C.c_int, [_vp, _vp]),
     "gpuar_b200_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),
     "gpuar_b200_ipc_close": (C.c_int, [_vp]),

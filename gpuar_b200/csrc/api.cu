@@ -398,6 +398,23 @@ int gpuar_b200_device_alloc(size_t bytes, void **d_ptr)
 
 int gpuar_b200_device_free(void *d_ptr) { return ck(cudaFree(d_ptr)); }
 
+int gpuar_b200_host_alloc(size_t bytes, void **h_ptr)
+{
+    if (!h_ptr) return GPUAR_E_ARG;
+    return ck(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+}
+
+int gpuar_b200_host_free(void *h_ptr) { return ck(cudaFreeHost(h_ptr)); }
+
+int gpuar_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int gpuar_b200_set_device(int device) { return ck(cudaSetDevice(device)); }
+
 int gpuar_b200_ipc_export(const void *d_ptr, uint8_t handle[64])
 {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");

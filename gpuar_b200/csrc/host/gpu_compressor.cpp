@@ -1,0 +1,174 @@
+// gpu_compressor.cpp -- the GPU path of the CLI: large page-locked segments in, one library call
+// per segment (the library overlaps H2D, kernels and D2H internally), header written last.
+//
+// Replaces the reference's per-packet pipeline (src/gpu_compressor.cpp:84-395: one 8 KiB
+// cudaMemcpyAsync + stream sync + fwrite per packet, host-side compaction, host-side chain walk).
+#include "gpu_compressor.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+#include "../../../include/gpuar_b200.h"
+
+namespace gip {
+
+static void check(int rc, const char *what)
+{
+    if (rc != 0) throw std::runtime_error(std::string(what) + ": " + gpuar_b200_strerror(rc));
+}
+
+GpuCompressor::GpuCompressor(std::size_t segmentBytes) : segmentBytes_(std::max<std::size_t>(kPacketBytes, segmentBytes / kPacketBytes * kPacketBytes))
+{
+    check(gpuar_b200_init(), "gpuar_b200_init");                // replaces initConstantRange(), gpu_compressor.cpp:19
+}
+
+GpuCompressor::~GpuCompressor()
+{
+    if (in_) gpuar_b200_host_free(in_);
+    if (out_) gpuar_b200_host_free(out_);
+}
+
+void GpuCompressor::chooseDevice(int id)
+{
+    check(gpuar_b200_set_device(id), "gpuar_b200_set_device");
+    check(gpuar_b200_init(), "gpuar_b200_init");
+}
+
+void GpuCompressor::reserve(std::size_t inBytes, std::size_t outBytes)
+{
+    if (inBytes > inCap_) {
+        if (in_) gpuar_b200_host_free(in_);
+        in_ = nullptr;
+        check(gpuar_b200_host_alloc(inBytes, (void **)&in_), "gpuar_b200_host_alloc");
+        inCap_ = inBytes;
+    }
+    if (outBytes > outCap_) {
+        if (out_) gpuar_b200_host_free(out_);
+        out_ = nullptr;
+        check(gpuar_b200_host_alloc(outBytes, (void **)&out_), "gpuar_b200_host_alloc");
+        outCap_ = outBytes;
+    }
+}
+
+CompressionInfo GpuCompressor::compress(ProgressMonitor *monitor)
+{
+    CompressionInfo info;
+    StopWatch io, proc;
+    monitor->reset();
+    File in(openFileName, "rb"), out(saveFileName, "wb");
+
+    io.start();
+    info.uncompressedFileSize = in.size();
+    std::uint8_t header[kFileHeader] = {0};
+    if (std::fwrite(header, kFileHeader, 1, out.get()) != 1) throw std::runtime_error("Write data to file failed");
+    io.stop();
+    info.compressedFileSize = kFileHeader;
+
+    const std::size_t seg = std::min<std::size_t>(segmentBytes_, std::max<std::size_t>(info.uncompressedFileSize, 1));
+    reserve(seg + 16, kFileHeader + gpuar_b200_payload_bound(seg));
+    for (;;) {
+        io.start();
+        const std::size_t got = std::fread(in_, 1, seg, in.get());
+        io.stop();
+        if (!got) break;
+        proc.start();
+        std::size_t image = 0;
+        check(gpuar_b200_compress_host(in_, got, out_, outCap_, &image), "gpuar_b200_compress_host");
+        proc.stop();
+        io.start();
+        const std::size_t payload = image - kFileHeader;       // the per-segment header is dropped:
+        if (payload && std::fwrite(out_ + kFileHeader, payload, 1, out.get()) != 1)   // packets are self-delimiting
+            throw std::runtime_error("Write compressed data to output file failed");
+        io.stop();
+        info.processedUncompressedSize += got;
+        info.compressedFileSize += payload;
+        monitor->updateProgress(&info);
+        if (got < seg) break;
+    }
+
+    io.start();                                                  // header last, as gpu_compressor.cpp:199-208
+    gpuar_b200_write_header(header, info.uncompressedFileSize, info.compressedFileSize);
+    if (std::fseek(out.get(), 0, SEEK_SET) != 0 || std::fwrite(header, kFileHeader, 1, out.get()) != 1)
+        throw std::runtime_error("Write data to file failed");
+    io.stop();
+    info.processTime = proc.ms();
+    info.ioTime = io.ms();
+    return info;
+}
+
+CompressionInfo GpuCompressor::decompress(ProgressMonitor *monitor)
+{
+    CompressionInfo info;
+    StopWatch io, proc;
+    monitor->reset();
+    File in(openFileName, "rb"), out(saveFileName, "wb");
+
+    io.start();
+    const std::uint64_t fileBytes = in.size();
+    std::uint8_t header[kFileHeader];
+    if (fileBytes < kFileHeader || std::fread(header, kFileHeader, 1, in.get()) != 1)
+        throw std::runtime_error("Incorrect file format");
+    io.stop();
+    if (gpuar_b200_check_header(header) != 0) throw std::runtime_error("Incorrect file format");
+    info.compressedFileSize = fileBytes;
+    std::uint64_t announced = 0;
+    for (int k = 0; k < 4; ++k) announced |= (std::uint64_t)header[4 + k] << (8 * k);   // low 32 bits are what the reference defines
+    info.uncompressedFileSize = announced;
+
+    // Segments of whole packets: the host only hops over compLen fields to find where to cut
+    // (one u16 per packet); the packets themselves are indexed and decoded on the device.
+    const std::size_t segPayload = segmentBytes_ + segmentBytes_ / 16;
+    reserve(kFileHeader + segPayload + kSlotBytes + 64, segmentBytes_ + 4 * kPacketBytes);
+    // window [begin, end) of the staging buffer holds payload bytes not yet decoded
+    std::size_t begin = 0, end = 0;
+    std::uint64_t remaining = fileBytes - kFileHeader;
+    std::uint64_t produced = 0;
+    std::uint8_t *const pay = in_ + kFileHeader;
+    while (remaining || end > begin) {
+        if (begin && (end - begin < kSlotBytes || begin > segPayload / 2)) {      // make room at the tail
+            std::memmove(pay, pay + begin, end - begin);
+            end -= begin;
+            begin = 0;
+        }
+        io.start();
+        const std::size_t want = (std::size_t)std::min<std::uint64_t>(remaining, segPayload - end);
+        if (want && std::fread(pay + end, 1, want, in.get()) != want) throw std::runtime_error("Invalid file length");
+        io.stop();
+        remaining -= want;
+        end += want;
+        // cut after the last complete packet; bound the raw size so the output staging cannot overflow
+        std::size_t cut = begin, raw = 0;
+        while (cut + 4 <= end) {
+            const std::size_t len = (std::size_t)pay[cut] | ((std::size_t)pay[cut + 1] << 8);
+            const std::size_t r = (std::size_t)pay[cut + 2] | ((std::size_t)pay[cut + 3] << 8);
+            if (len <= 4 || r > kPacketBytes) throw std::runtime_error("Incorrect file format");
+            if (cut + len > end || raw + r > segmentBytes_ + kPacketBytes) break;
+            cut += len;
+            raw += r;
+        }
+        if (cut == begin) throw std::runtime_error(remaining ? "Incorrect file format" : "Invalid file length");
+        proc.start();
+        std::uint8_t *image = pay + begin - kFileHeader;         // a .gip image of just this segment
+        gpuar_b200_write_header(image, raw, kFileHeader + (cut - begin));
+        std::size_t got = 0;
+        check(gpuar_b200_decompress_host(image, kFileHeader + (cut - begin), out_, outCap_, &got),
+              "gpuar_b200_decompress_host");
+        proc.stop();
+        if (got != raw) throw std::runtime_error("Incorrect file format");
+        io.start();
+        if (got && std::fwrite(out_, got, 1, out.get()) != 1)
+            throw std::runtime_error("Write uncompressed data to output file failed");
+        io.stop();
+        begin = cut;
+        produced += got;
+        info.processedUncompressedSize = produced;
+        if (produced > info.uncompressedFileSize) info.uncompressedFileSize = produced;
+        monitor->updateProgress(&info);
+    }
+    info.uncompressedFileSize = produced;
+    info.processTime = proc.ms();
+    info.ioTime = io.ms();
+    return info;
+}
+
+}  // namespace gip

@@ -1,0 +1,108 @@
+// main.cpp -- the `gpuar` command line, same surface as the reference (src/main.cpp:83-107,
+// SURVEY App. E): `c` / `d`, --in, --out, --host, --device, --nointeractive, --help.
+// Both --in=file and "--in file" are accepted.  Differences: the device is really selected;
+// without a CUDA device and without --host the program fails instead of silently coding on the
+// CPU (main.cpp:142-146); errors exit with status 1.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <string>
+
+#include "../../../include/gpuar_b200.h"
+#include "cpu_compressor.hpp"
+#include "gpu_compressor.hpp"
+
+using namespace gip;
+
+namespace {
+
+void usage()
+{
+    std::cout << "Usage: gpuar [options] --in=inputfile --out=outputfile\n\n"
+                 "where options include:\n"
+                 "c               compress input file (default)\n"
+                 "d               decompress input file\n"
+                 "--in            input file\n"
+                 "--out           output file (default output.gip)\n"
+                 "--help          print this help message\n"
+                 "--host          run the codec on the host CPU (single thread), otherwise on the CUDA device\n"
+                 "--device=N      CUDA device to use (default 0)\n"
+                 "--segment=MiB   raw bytes handed to the device per call (default 1024)\n"
+                 "--nointeractive accepted for compatibility\n";
+}
+
+// value of --name=value or "--name value"; empty if absent
+bool option(int argc, char **argv, const char *name, std::string &value)
+{
+    const std::string key = std::string("--") + name;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (a == key && i + 1 < argc) { value = argv[i + 1]; return true; }
+        if (a.compare(0, key.size() + 1, key + "=") == 0) { value = a.substr(key.size() + 1); return true; }
+    }
+    return false;
+}
+
+bool flag(int argc, char **argv, const char *name)
+{
+    for (int i = 1; i < argc; ++i)
+        if (std::strcmp(argv[i], name) == 0) return true;
+    return false;
+}
+
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    if (argc <= 1 || flag(argc, argv, "--help")) {
+        usage();
+        return 0;
+    }
+    try {
+        const bool decompress = flag(argc, argv, "d");          // main.cpp:102: anything else compresses
+        const bool hostMode = flag(argc, argv, "--host");
+        std::string inName, outName = "output.gip", value;
+        if (!option(argc, argv, "in", inName)) throw std::runtime_error("Please specify the input file name by command: --in filename");
+        option(argc, argv, "out", outName);
+        int device = 0;
+        if (option(argc, argv, "device", value)) device = std::atoi(value.c_str());
+        std::size_t segment = (std::size_t)1 << 30;
+        if (option(argc, argv, "segment", value)) segment = (std::size_t)std::atoll(value.c_str()) << 20;
+
+        std::unique_ptr<Compressor> compressor;
+        if (hostMode) {
+            std::cout << "Attention: execute kernel code on host." << std::endl;
+            compressor.reset(new CpuCompressor());
+        } else {
+            if (gpuar_b200_device_count() <= 0)
+                throw std::runtime_error("no CUDA device found (use --host to run the codec on the CPU)");
+            auto *gpu = new GpuCompressor(segment);
+            compressor.reset(gpu);
+            if (device > 0) {
+                std::cout << "Choose CUDA device: " << device << "." << std::endl;
+                gpu->chooseDevice(device);
+            }
+        }
+        compressor->setOpenFileName(inName);
+        compressor->setSaveFileName(outName);
+        ProgressMonitor monitor;
+        CompressionInfo info;
+        std::cout << "Start to " << (decompress ? "decompress " : "compress ") << inName << " to " << outName << "." << std::endl;
+        info = decompress ? compressor->decompress(&monitor) : compressor->compress(&monitor);
+
+        const double ratio = info.uncompressedFileSize ? (double)info.compressedFileSize / (double)info.uncompressedFileSize : 0.0;
+        std::cout << "Complete\n\nStatistics: \n"                                     // main.cpp:172-182
+                  << "Uncompressed file size " << info.uncompressedFileSize << " bytes\n"
+                  << "Compressed file size  " << info.compressedFileSize << " bytes\n"
+                  << "Compression ratio     " << ratio << "\n"
+                  << "Compute time          " << info.processTime / 1000 << " s\n"
+                  << "I/O time              " << info.ioTime / 1000 << " s\n"
+                  << "Score                 " << (1000 / (std::pow(ratio, 0.6) * std::pow(info.processTime / 1000, 0.4))) << std::endl;
+    } catch (const std::exception &e) {
+        std::cerr << e.what() << std::endl;
+        return 1;
+    }
+    return 0;
+}

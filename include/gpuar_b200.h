@@ -126,6 +126,13 @@ int gpuar_b200_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, 
 /* plain cudaMalloc/cudaFree on the current device: IPC-exportable allocations for the gather buffer */
 int gpuar_b200_device_alloc(size_t bytes, void **d_ptr);
 int gpuar_b200_device_free(void *d_ptr);
+/* page-locked host staging buffers (replaces the cudaMallocHost calls of compressor.cpp:23-25 and
+ * gpu_compressor.cpp:62-63) and device selection (gpu_compressor.cpp:67-82), so that host code
+ * above this ABI needs no CUDA headers */
+int gpuar_b200_host_alloc(size_t bytes, void **h_ptr);
+int gpuar_b200_host_free(void *h_ptr);
+int gpuar_b200_device_count(void);
+int gpuar_b200_set_device(int device);
 int gpuar_b200_ipc_export(const void *d_ptr, uint8_t handle[64]);
 int gpuar_b200_ipc_open(const uint8_t handle[64], void **d_ptr);
 int gpuar_b200_ipc_close(void *d_ptr);
