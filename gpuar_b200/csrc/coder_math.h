@@ -87,22 +87,24 @@ GPUAR_HD void narrow_renorm(uint32_t &L, uint32_t &V, uint32_t lo, uint32_t hi, 
     V = (V1 << t) & 0x7FFFu;
 }
 
-// ---- encoder bit sink: MSB-first stream (gpuar_kernel.cu:128-151), flushed as 32-bit words
+// ---- encoder bit sink: MSB-first stream (gpuar_kernel.cu:128-151), flushed as 32-bit words.
+// Branch free: after appending, at most one whole word is ready; it is stored under a
+// predicate and the counters are advanced arithmetically.
 struct BitSink {
     uint64_t acc;
-    uint32_t nb;       // valid low bits of acc, < 32 between calls
-    uint32_t *wp;      // next word
-    uint32_t *end;     // one past the last writable whole word
+    uint32_t nb;        // valid low bits of acc, < 32 between calls
+    uint32_t widx;      // next word of the slot's bitstream
+    uint32_t wcap;      // writable words
+    uint32_t *words;    // first bitstream word of the slot (4-byte aligned)
 
     GPUAR_HD void put(uint32_t val, uint32_t len)    // len <= 32, val < 2^len
     {
         acc = (acc << len) | val;
         nb += len;
-        if (nb >= 32u) {
-            nb -= 32u;
-            if (wp < end) *wp = bswap32((uint32_t)(acc >> nb));
-            ++wp;
-        }
+        const uint32_t w = (uint32_t)(acc >> (nb & 31u));          // the oldest 32 bits when nb >= 32
+        if (nb >= 32u && widx < wcap) words[widx] = bswap32(w);
+        widx += nb >> 5;
+        nb &= 31u;
     }
 };
 
@@ -122,44 +124,52 @@ BitSink put_run(BitSink out, uint32_t bit, uint32_t n)    // by value: keeps the
 
 // Bits of one symbol: the top k bits of U1 with, right after the first of them, `pend`
 // inverted copies of it (gpuar_kernel.cu:325-336); then the underflow count carries on.
-// Common case (pend <= 16): one field of k + pend <= 32 bits, no branches.
-GPUAR_HD void emit_symbol(BitSink &out, uint32_t &pend, uint32_t k, uint32_t u, uint32_t U1)
+// emit_field builds the common case (pend <= 16) as one field of k + pend <= 32 bits without
+// branches; emit_long is the rare remainder.
+GPUAR_HD bool emit_is_long(uint32_t pend, uint32_t k) { return k != 0u && pend > 16u; }
+
+GPUAR_HD void emit_field(BitSink &out, uint32_t &pend, uint32_t k, uint32_t u, uint32_t U1)
 {
     const uint32_t b = U1 >> 15;
     const uint32_t km1 = k ? k - 1u : 0u;
     const uint32_t rest = (U1 >> (16u - k)) & ((1u << km1) - 1u);
-    uint32_t val, len;
-    if (k && pend > 16u) {                                         // rare: emit b and the run first
-        out.put(b, 1u);
-        out = put_run(out, b ^ 1u, pend);
-        val = rest;
-        len = km1;
-    } else {
-        const uint32_t head = (1u << (pend & 31u)) - (b ^ 1u);    // b, then pend x !b
-        val = (head << km1) | rest;
-        len = k ? k + pend : 0u;
-        val = k ? val : 0u;
-    }
+    const uint32_t head = (1u << (pend & 31u)) - (b ^ 1u);        // b, then pend x !b
+    const uint32_t val = k ? ((head << km1) | rest) : 0u;
+    const uint32_t len = k ? k + pend : 0u;
     out.put(val, len);
     pend = k ? u : pend + u;
 }
 
+GPUAR_HD void emit_long(BitSink &out, uint32_t &pend, uint32_t k, uint32_t u, uint32_t U1)   // k != 0, pend > 16
+{
+    const uint32_t b = U1 >> 15;
+    out.put(b, 1u);
+    out = put_run(out, b ^ 1u, pend);
+    out.put((U1 >> (16u - k)) & ((1u << (k - 1u)) - 1u), k - 1u);
+    pend = u;
+}
+
+GPUAR_HD void emit_symbol(BitSink &out, uint32_t &pend, uint32_t k, uint32_t u, uint32_t U1)
+{
+    if (emit_is_long(pend, k)) emit_long(out, pend, k, u, U1);
+    else emit_field(out, pend, k, u, U1);
+}
+
 // End of packet: bit 14 of L, then pend+1 inverted copies (gpuar_kernel.cu:379-388); zero
-// padding to a byte (:430-439).  Returns the number of bitstream bytes; writes the tail
-// bytes and the 4-byte packet header (:525-528) at `slot`.
+// padding to a byte (:430-439).  Writes the tail bytes and the 4-byte packet header (:525-528)
+// at `slot` (out.words == slot + 4).  Returns compLen.
 GPUAR_HD uint32_t finish_packet(BitSink &out, uint32_t L, uint32_t pend, uint8_t *slot, uint32_t raw_len)
 {
-    uint32_t *const first = reinterpret_cast<uint32_t *>(slot + kHdr);
     const uint32_t b = (L >> 14) & 1u;
     out.put(b, 1u);
     out = put_run(out, b ^ 1u, pend + 1u);
-    uint32_t bytes = (uint32_t)(out.wp - first) * 4u;
+    uint32_t bytes = out.widx * 4u;
     if (out.nb) {
         const uint32_t tail = (out.nb + 7u) >> 3;
         const uint32_t w = (uint32_t)(out.acc << (32u - out.nb));  // left-aligned, zero padded
-        uint8_t *bp = reinterpret_cast<uint8_t *>(out.wp);
-        for (uint32_t t = 0; t < tail; ++t)
-            if (bp + t < reinterpret_cast<uint8_t *>(out.end)) bp[t] = (uint8_t)(w >> (24u - 8u * t));
+        uint8_t *bp = reinterpret_cast<uint8_t *>(out.words + out.widx);
+        if (out.widx < out.wcap)
+            for (uint32_t t = 0; t < tail; ++t) bp[t] = (uint8_t)(w >> (24u - 8u * t));
         bytes += tail;
     }
     const uint32_t comp = bytes + kHdr;
@@ -187,11 +197,15 @@ GPUAR_HD uint32_t unscale(uint32_t code, uint32_t L, uint32_t V, uint32_t T)
     return q;
 }
 
-// byte permute of the 8 bytes {b:a} (prmt.b32, default mode; selector nibbles 0..7)
+// byte permute of the 8 bytes {b:a} (prmt.b32, default mode).  Selector nibbles 0..7 pick a
+// byte; nibbles with bit 3 set (which the hardware turns into sign replication) only ever
+// occur in result bytes the callers ignore, so the host emulation may differ there.
 GPUAR_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
 #if defined(__CUDA_ARCH__)
-    return __byte_perm(a, b, sel);
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
 #else
     const uint64_t v = ((uint64_t)b << 32) | a;
     uint32_t r = 0;
@@ -270,37 +284,52 @@ GPUAR_HD uint32_t tree_decode(uint64_t &root, uint64_t *nodes, uint32_t stride, 
     return idx;
 }
 
-// Encoder side of the same model: the symbol is known, so the four child indices are its
-// bit pairs and the four node loads are independent of each other.  Returns lo = cum[s],
-// cnt = count[s] as they were before this symbol, and bumps count[s]
+// Encoder side of the model (own tree, own leaf format).  The symbol is known, so the child
+// indices are its bit pairs and the node loads are independent of each other.
+//   levels 0-2: W-form nodes (0, t0, t1, t2) as in the decoder: slot c = count below child c;
+//               slot 0 is constant zero, which also provides the zero bytes for the permute.
+//   level 3   : four plain counts (n0, n1, n2, n3) of the node's four symbols.
+// Returns lo = cum[s], cnt = count[s] before this symbol and bumps count[s]
 // (getRange(LOWER/UPPER) + update, gpuar_kernel.cu:215-238,272,279,288).
-GPUAR_HD void tree_step_known(uint64_t &node, uint32_t c, uint32_t &lo, uint32_t &tot)
+GPUAR_HD uint64_t enc_leaf_init() { return 0x0001000100010001ull; }
+
+GPUAR_HD void enc_tree_init(uint64_t &root, uint64_t *nodes, uint32_t stride)
 {
-    const uint32_t p = prmt((uint32_t)node, (uint32_t)(node >> 32), 0x3210u + 0x2222u * c);  // slot c | slot c+1 << 16
-    const uint32_t below = p & 0xFFFFu;
-    const uint32_t above = c == 3u ? tot : (p >> 16);
-    lo += below;
-    tot = above - below;
-    node += 0x0001000100010000ull << (16u * c);
+    root = tree_node_init(64);
+    uint32_t n = 0;
+    for (uint32_t q = 0; q < 4; ++q, ++n) nodes[n * stride] = tree_node_init(16);
+    for (uint32_t q = 0; q < 16; ++q, ++n) nodes[n * stride] = tree_node_init(4);
+    for (uint32_t q = 0; q < 64; ++q, ++n) nodes[n * stride] = enc_leaf_init();
 }
 
-GPUAR_HD void tree_encode(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t s, uint32_t total,
-                          uint32_t &lo, uint32_t &cnt)
+GPUAR_HD uint32_t enc_upper(uint64_t &node, uint32_t c)          // slot c, then +1 on the slots above c
+{
+    const uint32_t below = prmt((uint32_t)node, (uint32_t)(node >> 32), 0x0010u + 0x0022u * c);
+    node += 0x0001000100010000ull << (16u * c);
+    return below;
+}
+
+GPUAR_HD void tree_encode(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t s, uint32_t &lo, uint32_t &cnt)
 {
     uint64_t *const p1 = nodes + (s >> 6) * stride;
     uint64_t *const p2 = nodes + (4u + (s >> 4)) * stride;
     uint64_t *const p3 = nodes + (20u + (s >> 2)) * stride;
     uint64_t n1 = *p1, n2 = *p2, n3 = *p3;
-    uint32_t acc = 0, tot = total;
-    tree_step_known(root, s >> 6, acc, tot);
-    tree_step_known(n1, (s >> 4) & 3u, acc, tot);
-    tree_step_known(n2, (s >> 2) & 3u, acc, tot);
-    tree_step_known(n3, s & 3u, acc, tot);
+    uint32_t acc = enc_upper(root, s >> 6);
+    acc += enc_upper(n1, (s >> 4) & 3u);
+    acc += enc_upper(n2, (s >> 2) & 3u);
+    // leaf: prefix sums of the four plain counts in W-form, then the same permute
+    const uint32_t c = s & 3u, l = (uint32_t)n3, h = (uint32_t)(n3 >> 32);
+    const uint32_t x = l * 0x10001u;                               // (n0, n0+n1)
+    const uint32_t s01 = x >> 16;
+    const uint32_t s012 = s01 + (h & 0xFFFFu);
+    acc += prmt(x << 16, s01 | (s012 << 16), 0x0010u + 0x0022u * c);
+    cnt = prmt(l, h, 0x3210u + 0x2222u * c) & 0xFFFFu;
+    n3 += 1ull << (16u * c);
     *p1 = n1;
     *p2 = n2;
     *p3 = n3;
     lo = acc;
-    cnt = tot;
 }
 
 // ---- decoder bit source: 64-bit reservoir, next bit = MSB, fed one 32-bit word at a time
@@ -315,6 +344,12 @@ struct BitSource {
         return bits;
     }
     GPUAR_HD bool hungry() const { return have <= 32u; }
+    GPUAR_HD void feed_if(bool hungry_now, uint32_t be_word)       // predicated form of feed()
+    {
+        const uint64_t add = (uint64_t)be_word << ((32u - have) & 63u);
+        buf |= hungry_now ? add : 0ull;
+        have += hungry_now ? 32u : 0u;
+    }
     GPUAR_HD void feed(uint32_t be_word)
     {
         buf |= (uint64_t)be_word << (32u - have);

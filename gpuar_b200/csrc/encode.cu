@@ -9,15 +9,20 @@
 // advance through their packets in lock step (position i of 32 different packets per
 // step), so the running total T = 256 + i -- the divisor of both interval divisions -- is
 // warp-uniform and becomes a multiply by a per-step reciprocal.  Per symbol:
-//   MODEL  cum[s], count[s] and count[s]++ from the packet's 4-ary cumulative-count tree
-//          in shared memory (coder_math.h: tree_encode): root in registers, three
-//          independent 8-byte loads/stores, byte permutes instead of branches.  Equals the
-//          reference's two Fenwick prefix sums + update (gpuar_kernel.cu:215-238).
+//   MODEL  cum[s], count[s] and count[s]++ from the packet's 4-ary count tree in shared
+//          memory (coder_math.h: tree_encode): root in registers, three independent 8-byte
+//          loads/stores, byte permutes instead of branches.  Equals the reference's two
+//          Fenwick prefix sums + update (gpuar_kernel.cu:215-238).
 //   CODER  the interval recurrence (gpuar_kernel.cu:256-288) and the renormalisation
-//          loop (:321-367) in closed form; bits go to a 64-bit accumulator flushed as
-//          32-bit words into the packet's slot.
-// The model does not depend on the coder state, so the model work of symbol i+1 overlaps
-// the dependent coder chain of symbol i inside each warp.
+//          loop (:321-367) in closed form.
+//   BITS   the step's output field appended to a 64-bit accumulator, flushed as 32-bit
+//          words into the packet's slot.
+// Only CODER is a loop-carried dependent chain.  The three stages are software pipelined
+// inside each lane -- iteration i runs BITS(i-1), CODER(i), MODEL(i+1), which are mutually
+// independent -- so the chain of one step overlaps the model and bit-packing work of its
+// neighbours even when a scheduler holds a single warp (64 MiB = 256 warps on 592 schedulers).
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "lookback.cuh"
@@ -40,7 +45,7 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
 
     uint64_t *const tree = &sm.tree[0][lane];
     uint64_t root;
-    tree_init(root, tree, 32u);                                   // all counts 1 (:403-419)
+    enc_tree_init(root, tree, 32u);                               // all counts 1 (:403-419)
 
     const size_t off = (size_t)my * kPacket;
     uint32_t len = 0;                                             // 8192 except for the last packet
@@ -53,22 +58,45 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
     BitSink out;
     out.acc = 0;
     out.nb = 0;
-    out.wp = reinterpret_cast<uint32_t *>(slot + kHdr);
-    out.end = reinterpret_cast<uint32_t *>(slot + (mine ? (slot_stride & ~3u) : 0u));
+    out.widx = 0;
+    out.wcap = mine ? ((slot_stride - kHdr) >> 2) : 0u;
+    out.words = reinterpret_cast<uint32_t *>(slot + kHdr);
 
     // 16 input bytes per lane per half round, fetched one half round ahead.  The read may
     // run up to 15 bytes past n inside the caller's 16-byte-rounded buffer (API contract).
     const uint4 *const in16 = reinterpret_cast<const uint4 *>(src + off);
-    auto fetch = [&](uint32_t h) -> uint4 {
-        return (h * 16u < len) ? __ldg(in16 + h) : make_uint4(0, 0, 0, 0);
+    auto fetch = [&](uint32_t g) -> uint4 {
+        return (g * 16u < len) ? __ldg(in16 + g) : make_uint4(0, 0, 0, 0);
     };
-    uint4 ahead = fetch(0);
+    uint4 cur = fetch(0), ahead = fetch(1);
 
-    auto step = [&](uint32_t i, uint32_t s, uint32_t m, uint32_t sh) {
-        uint32_t lo, cnt, k, u, U1;
-        tree_encode(root, tree, 32u, s, 256u + i, lo, cnt);
-        narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
-        emit_symbol(out, pend, k, u, U1);
+    // pipeline registers
+    uint32_t lo_n = 0, cnt_n = 1;            // MODEL output for the next CODER step
+    uint32_t pk = 0, pu = 0, pU = 0;         // CODER output not yet turned into bits
+    bool pending = false;
+    if (len) tree_encode(root, tree, 32u, cur.x & 0xFFu, lo_n, cnt_n);           // MODEL(0)
+
+    // iteration i: BITS(i-1), CODER(i), MODEL(i+1).  kFast: every lane has positions i and
+    // i+1 and a pending field, so nothing is predicated per lane.
+    auto iter = [&](auto fast_tag, uint32_t i, uint32_t s_next, uint32_t m, uint32_t sh) {
+        constexpr bool kFast = decltype(fast_tag)::value;
+        if (kFast) {
+            if (__any_sync(kFull, emit_is_long(pend, pk))) {      // warp-uniform and almost never taken
+                if (emit_is_long(pend, pk)) {
+                    emit_long(out, pend, pk, pu, pU);
+                    pk = 0;                                       // the field below becomes a no-op
+                    pu = 0;
+                }
+            }
+            emit_field(out, pend, pk, pu, pU);
+            narrow_renorm(L, V, lo_n, lo_n + cnt_n, m, sh, pk, pu, pU);
+            tree_encode(root, tree, 32u, s_next, lo_n, cnt_n);
+        } else {
+            if (pending) emit_symbol(out, pend, pk, pu, pU);
+            pending = i < len;
+            if (pending) narrow_renorm(L, V, lo_n, lo_n + cnt_n, m, sh, pk, pu, pU);
+            if (i + 1u < len) tree_encode(root, tree, 32u, s_next, lo_n, cnt_n);
+        }
     };
 
     const uint32_t rounds = (max_len + 31u) >> 5;
@@ -77,32 +105,35 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
         uint32_t sh;
         const uint32_t m_l = magic_for(256u + i0 + lane, sh);     // lane j holds the multiplier of step j
         sh = shift_for(256u + i0);                                // the shift is uniform over the round
-        const bool full = i0 + 32u <= min_len;                    // every lane has all 32 positions
+        // fast rounds: not the first (nothing pending yet at i = 0), and position i0+32 exists in every lane
+        const bool fast = r != 0u && i0 + 33u <= min_len;
 #pragma unroll 1
         for (uint32_t h = 0; h < 2u; ++h) {
-            const uint4 cur = ahead;
-            ahead = fetch(2u * r + h + 1u);
-            // 4 symbols per inner iteration: the loop body stays small enough for the
-            // instruction cache (a fully unrolled round is ~60 KB of SASS)
 #pragma unroll 1
             for (uint32_t q = 0; q < 4u; ++q) {
+                // 4 symbols per inner iteration keeps the loop body inside the instruction cache
                 const uint32_t word = q == 0u ? cur.x : q == 1u ? cur.y : q == 2u ? cur.z : cur.w;
+                const uint32_t next = q == 0u ? cur.y : q == 1u ? cur.z : q == 2u ? cur.w : ahead.x;
+                const uint32_t ahead_syms = (word >> 8) | (next << 24);       // symbols i+1 .. i+4
                 const uint32_t j0 = 16u * h + 4u * q;
-                if (full) {
+                if (fast) {
 #pragma unroll
                     for (uint32_t j = 0; j < 4u; ++j)
-                        step(i0 + j0 + j, (word >> (8u * j)) & 0xFFu, __shfl_sync(kFull, m_l, j0 + j), sh);
+                        iter(std::true_type{}, i0 + j0 + j, (ahead_syms >> (8u * j)) & 0xFFu,
+                             __shfl_sync(kFull, m_l, j0 + j), sh);
                 } else {
-                    // ragged tail: only the warp holding the last packet of the stream gets here
+                    // first round, last round, ragged tail: per-lane predicates
 #pragma unroll 1
-                    for (uint32_t j = 0; j < 4u; ++j) {
-                        const uint32_t m = __shfl_sync(kFull, m_l, j0 + j);
-                        if (i0 + j0 + j < len) step(i0 + j0 + j, (word >> (8u * j)) & 0xFFu, m, sh);
-                    }
+                    for (uint32_t j = 0; j < 4u; ++j)
+                        iter(std::false_type{}, i0 + j0 + j, (ahead_syms >> (8u * j)) & 0xFFu,
+                             __shfl_sync(kFull, m_l, j0 + j), sh);
                 }
             }
+            cur = ahead;
+            ahead = fetch(2u * r + h + 2u);
         }
     }
+    if (pending) emit_symbol(out, pend, pk, pu, pU);              // BITS of the last step
 
     if (mine) {
         const uint32_t comp = finish_packet(out, L, pend, slot, len);

@@ -12,17 +12,18 @@ using namespace gpuar;
 std::uint32_t cpuEncodePacket(const std::uint8_t *in, std::uint32_t n, std::uint8_t *slot)
 {
     std::uint64_t tree[kTreeStored], root;
-    tree_init(root, tree, 1);
+    enc_tree_init(root, tree, 1);
     std::uint32_t L = 0, V = 0, pend = 0;
     BitSink out;
     out.acc = 0;
     out.nb = 0;
-    out.wp = reinterpret_cast<std::uint32_t *>(slot + kHdr);
-    out.end = reinterpret_cast<std::uint32_t *>(slot + kSlot);
+    out.widx = 0;
+    out.wcap = (kSlot - kHdr) >> 2;
+    out.words = reinterpret_cast<std::uint32_t *>(slot + kHdr);
     for (std::uint32_t i = 0; i < n; ++i) {
         std::uint32_t sh, lo, cnt, k, u, U1;
         const std::uint32_t m = magic_for(256u + i, sh);
-        tree_encode(root, tree, 1, in[i], 256u + i, lo, cnt);
+        tree_encode(root, tree, 1, in[i], lo, cnt);
         narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
         emit_symbol(out, pend, k, u, U1);
     }

@@ -19,18 +19,19 @@ uint32_t host_model_encode_packet(const uint8_t *x, uint32_t n, uint8_t *slot, u
 {
     std::vector<uint64_t> tree(kTreeStored);
     uint64_t root;
-    tree_init(root, tree.data(), 1);
+    enc_tree_init(root, tree.data(), 1);
     uint32_t L = 0, V = 0, pend = 0;
     BitSink out;
     out.acc = 0;
     out.nb = 0;
-    out.wp = reinterpret_cast<uint32_t *>(slot + kHdr);
-    out.end = reinterpret_cast<uint32_t *>(slot + (slot_bytes & ~3u));
+    out.widx = 0;
+    out.wcap = (slot_bytes - kHdr) >> 2;
+    out.words = reinterpret_cast<uint32_t *>(slot + kHdr);
     for (uint32_t i = 0; i < n; ++i) {
         uint32_t sh;
         const uint32_t m = magic_for(256u + i, sh);
         uint32_t lo, cnt, k, u, U1;
-        tree_encode(root, tree.data(), 1, x[i], 256u + i, lo, cnt);
+        tree_encode(root, tree.data(), 1, x[i], lo, cnt);
         narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
         emit_symbol(out, pend, k, u, U1);
     }
