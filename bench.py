@@ -209,6 +209,7 @@ def run_ours(args):
             os.dup2(saved, 1)
             os.close(saved)
     dev = codec.DeviceCodec(local)
+    _lib.set_option(_lib.OPT_ENCODE_PATH, {"auto": 0, "fused": 1, "ws": 2}[args.encode_path])
     sharded = ShardedCodec(dev, rank, world)
 
     gen, seed, nbytes, desc = WORKLOADS[args.workload]
@@ -330,7 +331,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "u16", "data": "synthetic",
             "config": {"workload": args.workload, "desc": desc, "bytes_per_rank": nbytes, "packet_bytes": 8192,
                        "payload_bytes_rank0": c, "l2": "flushed between timed iterations (256 MiB write)",
-                       "parallelism": f"packet-range shards x{world}" if world > 1 else "single GPU"},
+                       "parallelism": f"packet-range shards x{world}" if world > 1 else "single GPU",
+                       "encode_path": args.encode_path},
             "decode": {"value": job / (t_dec / args.steps) / GB, "unit": "GB/s",
                        "ms_per_step": t_dec / args.steps * 1e3,
                        "includes": "device packet-chain discovery + decode kernel"},
@@ -363,6 +365,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="u64m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--encode-path", default="auto", choices=["auto", "fused", "ws"],
+                    help="encoder kernel: auto (by packet count), fused lane=packet, warp-specialised")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -60,6 +60,7 @@ SIGNATURES = {
     "initConstantRange": (None, []),
     "garCompressExecutor": (None, [_vp, _sz, _vp, C.c_uint32]),
     "garDecompressExecutor": (None, [_vp, _sz, _vp, C.c_uint32]),
+    "gpuar_b200_set_option": (C.c_int, [C.c_int, C.c_longlong]),
     "gpuar_b200_profile": (None, [C.c_int]),
     "gpuar_b200_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "gpuar_b200_launch_count": (C.c_uint64, []),
@@ -92,6 +93,14 @@ def strerror(code: int) -> str:
 def check(code: int, what: str) -> None:
     if code != 0:
         raise GpuarError(code, what)
+
+
+OPT_ENCODE_PATH, OPT_WS_MAX_PACKETS = 1, 2
+ENCODE_AUTO, ENCODE_FUSED, ENCODE_WS = 0, 1, 2
+
+
+def set_option(key: int, value: int) -> None:
+    check(lib().gpuar_b200_set_option(key, value), "gpuar_b200_set_option")
 
 
 SPANS = ("encode", "compact", "index", "decode")

@@ -38,6 +38,20 @@ static EncodePlan encode_plan(size_t n)
 
 static int ck(cudaError_t e) { return (int)e; }
 
+// ---- tuning knobs (gpuar_b200_set_option)
+static int g_encode_path = 0;                    // 0 auto, 1 fused lane=packet, 2 warp-specialised
+// auto: the warp-specialised kernel while the input is at most one resident wave of its CTAs
+static size_t g_ws_max_packets = (size_t)148 * 5 * 32;
+
+static cudaError_t encode_slots(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t stride, uint32_t *d_sizes,
+                                cudaStream_t st)
+{
+    const size_t packets = packets_of(n);
+    const bool ws = g_encode_path == 2 || (g_encode_path == 0 && packets <= g_ws_max_packets);
+    return ws ? launch_encode_slots_ws(d_in, n, d_slots, stride, d_sizes, st)
+              : launch_encode_slots(d_in, n, d_slots, stride, d_sizes, st);
+}
+
 // ---- optional per-kernel timing (bench.py's roofline): CUDA events recorded on the
 // caller's stream around each kernel of an entry point; off by default
 struct Span { cudaEvent_t a, b; int what; };
@@ -171,7 +185,7 @@ int gpuar_b200_encode(const uint8_t *d_in, size_t n, uint8_t *d_payload, size_t 
     cudaError_t e;
     {
         Scope t(GPUAR_SPAN_ENCODE, st);
-        e = launch_encode_slots(d_in, n, s + p.off_slots, kSlot, sizes, st);
+        e = encode_slots(d_in, n, s + p.off_slots, kSlot, sizes, st);
     }
     if (e != cudaSuccess) return ck(e);
     {
@@ -203,6 +217,23 @@ int gpuar_b200_decode(const uint8_t *d_payload, size_t c, const uint64_t *d_offs
     Scope t(GPUAR_SPAN_DECODE, (cudaStream_t)stream);
     return ck(launch_decode(d_payload, c + GPUAR_PAD_BYTES, d_offsets, 0, (uint32_t)n_packets, d_out,
                             (cudaStream_t)stream));
+}
+
+/* ------------------------------------------------------------------- options */
+int gpuar_b200_set_option(int key, long long value)
+{
+    switch (key) {
+    case GPUAR_OPT_ENCODE_PATH:
+        if (value < 0 || value > 2) return GPUAR_E_ARG;
+        g_encode_path = (int)value;
+        return 0;
+    case GPUAR_OPT_WS_MAX_PACKETS:
+        if (value < 0) return GPUAR_E_ARG;
+        g_ws_max_packets = (size_t)value;
+        return 0;
+    default:
+        return GPUAR_E_ARG;
+    }
 }
 
 /* ----------------------------------------------------------------- profiling */
@@ -440,7 +471,7 @@ void initConstantRange(void) { (void)gpuar_b200_init(); }
 void garCompressExecutor(const uint8_t *source, size_t size, uint8_t *destination, uint32_t numBlocks)
 {
     (void)numBlocks;
-    (void)launch_encode_slots(source, size, destination, kSlot, nullptr, (cudaStream_t)0);
+    (void)encode_slots(source, size, destination, kSlot, nullptr, (cudaStream_t)0);
 }
 
 void garDecompressExecutor(const uint8_t *source, size_t size, uint8_t *destination, uint32_t numBlocks)

@@ -309,15 +309,25 @@ GPUAR_HD uint32_t enc_upper(uint64_t &node, uint32_t c)          // slot c, then
     return below;
 }
 
-GPUAR_HD void tree_encode(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t s, uint32_t &lo, uint32_t &cnt)
+// The levels are independent of each other given the symbol, so the model can be split:
+// levels 0-1 (root + 4 nodes) and levels 2-3 (16 nodes + 64 leaves).  cum[s] is the sum
+// of the two partial results.
+GPUAR_HD uint32_t tree_encode_upper(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t s)
 {
     uint64_t *const p1 = nodes + (s >> 6) * stride;
-    uint64_t *const p2 = nodes + (4u + (s >> 4)) * stride;
-    uint64_t *const p3 = nodes + (20u + (s >> 2)) * stride;
-    uint64_t n1 = *p1, n2 = *p2, n3 = *p3;
+    uint64_t n1 = *p1;
     uint32_t acc = enc_upper(root, s >> 6);
     acc += enc_upper(n1, (s >> 4) & 3u);
-    acc += enc_upper(n2, (s >> 2) & 3u);
+    *p1 = n1;
+    return acc;
+}
+
+GPUAR_HD uint32_t tree_encode_lower(uint64_t *nodes, uint32_t stride, uint32_t s, uint32_t &cnt)
+{
+    uint64_t *const p2 = nodes + (4u + (s >> 4)) * stride;
+    uint64_t *const p3 = nodes + (20u + (s >> 2)) * stride;
+    uint64_t n2 = *p2, n3 = *p3;
+    uint32_t acc = enc_upper(n2, (s >> 2) & 3u);
     // leaf: prefix sums of the four plain counts in W-form, then the same permute
     const uint32_t c = s & 3u, l = (uint32_t)n3, h = (uint32_t)(n3 >> 32);
     const uint32_t x = l * 0x10001u;                               // (n0, n0+n1)
@@ -326,10 +336,15 @@ GPUAR_HD void tree_encode(uint64_t &root, uint64_t *nodes, uint32_t stride, uint
     acc += prmt(x << 16, s01 | (s012 << 16), 0x0010u + 0x0022u * c);
     cnt = prmt(l, h, 0x3210u + 0x2222u * c) & 0xFFFFu;
     n3 += 1ull << (16u * c);
-    *p1 = n1;
     *p2 = n2;
     *p3 = n3;
-    lo = acc;
+    return acc;
+}
+
+GPUAR_HD void tree_encode(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t s, uint32_t &lo, uint32_t &cnt)
+{
+    const uint32_t up = tree_encode_upper(root, nodes, stride, s);
+    lo = up + tree_encode_lower(nodes, stride, s, cnt);
 }
 
 // ---- decoder bit source: 64-bit reservoir, next bit = MSB, fed one 32-bit word at a time

@@ -68,13 +68,13 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
     auto fetch = [&](uint32_t g) -> uint4 {
         return (g * 16u < len) ? __ldg(in16 + g) : make_uint4(0, 0, 0, 0);
     };
-    uint4 cur = fetch(0), ahead = fetch(1);
+    uint4 bufA = fetch(0), bufB = fetch(1);                       // chunks 2r and 2r+1 at the top of round r
 
     // pipeline registers
     uint32_t lo_n = 0, cnt_n = 1;            // MODEL output for the next CODER step
     uint32_t pk = 0, pu = 0, pU = 0;         // CODER output not yet turned into bits
     bool pending = false;
-    if (len) tree_encode(root, tree, 32u, cur.x & 0xFFu, lo_n, cnt_n);           // MODEL(0)
+    if (len) tree_encode(root, tree, 32u, bufA.x & 0xFFu, lo_n, cnt_n);          // MODEL(0)
 
     // iteration i: BITS(i-1), CODER(i), MODEL(i+1).  kFast: every lane has positions i and
     // i+1 and a pending field, so nothing is predicated per lane.
@@ -99,6 +99,30 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
         }
     };
 
+    // 16 symbols held in `c`; `nx` = the word that follows them (first word of the next chunk)
+    auto half = [&](const uint4 &c, uint32_t nx, bool fast, uint32_t i0, uint32_t h, uint32_t m_l, uint32_t sh) {
+#pragma unroll 1
+        for (uint32_t q = 0; q < 4u; ++q) {
+            // 4 symbols per inner iteration keeps the loop body inside the instruction cache
+            const uint32_t word = q == 0u ? c.x : q == 1u ? c.y : q == 2u ? c.z : c.w;
+            const uint32_t next = q == 0u ? c.y : q == 1u ? c.z : q == 2u ? c.w : nx;
+            const uint32_t ahead_syms = (word >> 8) | (next << 24);           // symbols i+1 .. i+4
+            const uint32_t j0 = 16u * h + 4u * q;
+            if (fast) {
+#pragma unroll
+                for (uint32_t j = 0; j < 4u; ++j)
+                    iter(std::true_type{}, i0 + j0 + j, (ahead_syms >> (8u * j)) & 0xFFu,
+                         __shfl_sync(kFull, m_l, j0 + j), sh);
+            } else {
+                // first round, last round, ragged tail: per-lane predicates
+#pragma unroll 1
+                for (uint32_t j = 0; j < 4u; ++j)
+                    iter(std::false_type{}, i0 + j0 + j, (ahead_syms >> (8u * j)) & 0xFFu,
+                         __shfl_sync(kFull, m_l, j0 + j), sh);
+            }
+        }
+    };
+
     const uint32_t rounds = (max_len + 31u) >> 5;
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t i0 = r * 32u;
@@ -107,31 +131,10 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
         sh = shift_for(256u + i0);                                // the shift is uniform over the round
         // fast rounds: not the first (nothing pending yet at i = 0), and position i0+32 exists in every lane
         const bool fast = r != 0u && i0 + 33u <= min_len;
-#pragma unroll 1
-        for (uint32_t h = 0; h < 2u; ++h) {
-#pragma unroll 1
-            for (uint32_t q = 0; q < 4u; ++q) {
-                // 4 symbols per inner iteration keeps the loop body inside the instruction cache
-                const uint32_t word = q == 0u ? cur.x : q == 1u ? cur.y : q == 2u ? cur.z : cur.w;
-                const uint32_t next = q == 0u ? cur.y : q == 1u ? cur.z : q == 2u ? cur.w : ahead.x;
-                const uint32_t ahead_syms = (word >> 8) | (next << 24);       // symbols i+1 .. i+4
-                const uint32_t j0 = 16u * h + 4u * q;
-                if (fast) {
-#pragma unroll
-                    for (uint32_t j = 0; j < 4u; ++j)
-                        iter(std::true_type{}, i0 + j0 + j, (ahead_syms >> (8u * j)) & 0xFFu,
-                             __shfl_sync(kFull, m_l, j0 + j), sh);
-                } else {
-                    // first round, last round, ragged tail: per-lane predicates
-#pragma unroll 1
-                    for (uint32_t j = 0; j < 4u; ++j)
-                        iter(std::false_type{}, i0 + j0 + j, (ahead_syms >> (8u * j)) & 0xFFu,
-                             __shfl_sync(kFull, m_l, j0 + j), sh);
-                }
-            }
-            cur = ahead;
-            ahead = fetch(2u * r + h + 2u);
-        }
+        half(bufA, bufB.x, fast, i0, 0u, m_l, sh);
+        bufA = fetch(2u * r + 2u);                                // consumed 12+ steps from now
+        half(bufB, bufA.x, fast, i0, 1u, m_l, sh);
+        bufB = fetch(2u * r + 3u);
     }
     if (pending) emit_symbol(out, pend, pk, pu, pU);              // BITS of the last step
 

@@ -10,6 +10,9 @@ namespace gpuar {
 const void *probe_kernel();   // address of a kernel of this library, for image-loadability checks
 cudaError_t launch_encode_slots(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t slot_stride,
                                 uint32_t *d_sizes, cudaStream_t st);
+// encode_ws.cu: same contract, three warps per 32 packets (for inputs that cannot fill the GPU)
+cudaError_t launch_encode_slots_ws(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t slot_stride,
+                                   uint32_t *d_sizes, cudaStream_t st);
 size_t compact_desc_bytes(size_t packets);
 cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const uint32_t *d_sizes,
                            uint32_t packets, uint8_t *d_payload, uint64_t *d_desc, uint64_t *d_total,

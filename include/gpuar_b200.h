@@ -148,6 +148,15 @@ void initConstantRange(void);
 void garCompressExecutor(const uint8_t *source, size_t size, uint8_t *destination, uint32_t numBlocks);
 void garDecompressExecutor(const uint8_t *source, size_t size, uint8_t *destination, uint32_t numBlocks);
 
+/* ------------------------------------------------------------------- options
+ * The encoder has two kernels with identical output: lane = packet with the three stages of a
+ * step software-pipelined in one warp (best when packets >> warp schedulers), and a
+ * warp-specialised one (model / coder / bit-packing warps per 32 packets; best for small
+ * inputs).  Default: chosen by packet count. */
+#define GPUAR_OPT_ENCODE_PATH 1      /* 0 auto (default), 1 fused, 2 warp-specialised */
+#define GPUAR_OPT_WS_MAX_PACKETS 2   /* auto: use the warp-specialised kernel up to this many packets */
+int gpuar_b200_set_option(int key, long long value);
+
 /* ----------------------------------------------------------- measurement hooks
  * gpuar_b200_profile(1) makes encode/index/decode record CUDA events on the caller's
  * stream around each kernel group; gpuar_b200_profile_read waits for the recorded spans,

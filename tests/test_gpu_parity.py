@@ -76,6 +76,25 @@ def test_encode_long_underflow_runs(dev):
     assert np.array_equal(dev_encode(dev, data), O.encode(data))
 
 
+@pytest.mark.parametrize("path", ["fused", "ws"])
+def test_both_encode_kernels_are_bit_exact(dev, path):
+    """The lane=packet kernel and the warp-specialised kernel must produce identical slots/payloads."""
+    from gpuar_b200 import _lib
+    _lib.set_option(_lib.OPT_ENCODE_PATH, _lib.ENCODE_FUSED if path == "fused" else _lib.ENCODE_WS)
+    try:
+        for n in (1, 31, 32, 33, 64, 65, 8191, 8192, 8193, 8192 * 31 + 5, 8192 * 32, 8192 * 70 + 4097):
+            for data in (D.uniform(n + 1, n), D.and3(n + 2, n), D.zeros(n)):
+                assert np.array_equal(dev_encode(dev, data), O.encode(data)), (path, n)
+        rng = np.random.default_rng(7)
+        data = rng.choice(np.array([127, 128], np.uint8), size=8192 * 40, p=[0.5, 0.5])   # long underflow runs
+        assert np.array_equal(dev_encode(dev, data), O.encode(data))
+        for name in ("m1m", "u1m_tail", "rr", "adv"):
+            data = make_input(VECTORS[name])
+            assert md5(dev_encode(dev, data)) == VECTORS[name]["payload_md5"]
+    finally:
+        _lib.set_option(_lib.OPT_ENCODE_PATH, _lib.ENCODE_AUTO)
+
+
 # ------------------------------------------------------------------ index
 @pytest.mark.parametrize("name", SMALL)
 def test_index_equals_chain_walk(dev, name):
