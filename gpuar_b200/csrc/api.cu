@@ -384,8 +384,12 @@ int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *ou
     if ((uint32_t)raw != (uint32_t)total) return GPUAR_E_FORMAT;    // header field, file_header.hpp:61-66
     if (total > out_cap || !out) return GPUAR_E_ARG;
 
-    // decode in packet ranges; the D2H of range k overlaps the decode of range k+1
-    const size_t step = 4096;                                       // packets per range (32 MiB)
+    // decode in packet ranges; the D2H of range k overlaps the decode of range k+1.  A range is one
+    // resident wave of the decode kernel (10 lane=packet warps per SM): anything smaller takes just
+    // as long, because a packet is a serial chain.
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const size_t step = (size_t)sms * 10 * 32;                      // packets per range (370 MiB on B200)
     for (size_t p0 = 0, k = 0; p0 < packets; p0 += step, ++k) {
         const size_t m = (packets - p0 < step) ? packets - p0 : step;
         uint8_t *d_out = (uint8_t *)h->big_out.p + p0 * kPacket;

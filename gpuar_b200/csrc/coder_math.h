@@ -347,37 +347,67 @@ GPUAR_HD void tree_encode(uint64_t &root, uint64_t *nodes, uint32_t stride, uint
     lo = up + tree_encode_lower(nodes, stride, s, cnt);
 }
 
-// ---- decoder bit source: 64-bit reservoir, next bit = MSB, fed one 32-bit word at a time
+// ---- funnel shifts (shf.l / shf.r.clamp) with host fall-backs
+GPUAR_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s)      // upper 32 bits of {hi:lo} << s, s in 0..31
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    return (uint32_t)(((((uint64_t)hi << 32) | lo) << (s & 31u)) >> 32);
+#endif
+}
+GPUAR_HD uint32_t shr_clamp(uint32_t x, uint32_t s)                    // x >> s with s in 0..32 (32 gives 0)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_rc(x, 0u, s);
+#else
+    return s >= 32u ? 0u : x >> s;
+#endif
+}
+
+// ---- decoder bit source: 64-bit window {hi:lo}, next stream bit = MSB of hi, fed one 32-bit
+// word at a time.  `have` = valid bits; >= 33 at the top of every step, so hi is always whole.
 struct BitSource {
-    uint64_t buf;
-    uint32_t have;     // valid bits in buf; >= 33 at the top of every step
+    uint32_t hi, lo;
+    uint32_t have;
+    GPUAR_HD void start(uint64_t window, uint32_t valid)
+    {
+        hi = (uint32_t)(window >> 32);
+        lo = (uint32_t)window;
+        have = valid;
+    }
+    GPUAR_HD void skip(uint32_t t)                   // t <= 31
+    {
+        hi = funnel_l(lo, hi, t);
+        lo <<= t;
+        have -= t;
+    }
     GPUAR_HD uint32_t take(uint32_t t)               // t <= 31
     {
-        const uint32_t bits = (uint32_t)((buf >> 1) >> (63u - t));
-        buf <<= t;
-        have -= t;
+        const uint32_t bits = funnel_l(hi, 0u, t);
+        skip(t);
         return bits;
     }
     GPUAR_HD bool hungry() const { return have <= 32u; }
-    GPUAR_HD void feed_if(bool hungry_now, uint32_t be_word)       // predicated form of feed()
+    GPUAR_HD void feed_if(bool on, uint32_t be_word)  // requires have <= 32 when on: lo is empty then
     {
-        const uint64_t add = (uint64_t)be_word << ((32u - have) & 63u);
-        buf |= hungry_now ? add : 0ull;
-        have += hungry_now ? 32u : 0u;
+        const uint32_t add_hi = shr_clamp(be_word, have);
+        const uint32_t add_lo = be_word << ((32u - have) & 31u);
+        hi |= on ? add_hi : 0u;
+        lo = on ? add_lo : lo;
+        have += on ? 32u : 0u;
     }
-    GPUAR_HD void feed(uint32_t be_word)
-    {
-        buf |= (uint64_t)be_word << (32u - have);
-        have += 32u;
-    }
+    GPUAR_HD void feed(uint32_t be_word) { feed_if(true, be_word); }
 };
 
 // readEncodedBits in closed form (:787-836): shift in k+u bits; an underflow run leaves
-// the MSB flipped.
+// the MSB flipped.  One funnel shift moves the bits from the window into the code register.
 GPUAR_HD uint32_t advance_code(uint32_t code, uint32_t k, uint32_t u, BitSource &in)
 {
     const uint32_t t = k + u;
-    return (((code << t) | in.take(t)) & 0xFFFFu) ^ (u ? 0x8000u : 0u);
+    const uint32_t next = (funnel_l(in.hi, code, t) & 0xFFFFu) ^ (u ? 0x8000u : 0u);
+    in.skip(t);
+    return next;
 }
 
 }  // namespace gpuar

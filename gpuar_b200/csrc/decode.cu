@@ -50,8 +50,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     uint32_t ahead = 0;             // prefetched word, still little-endian: swapped when fed, so that
                                     // nothing waits on the load until the reservoir needs it
     BitSource in;
-    in.buf = 0;
-    in.have = 64u;
+    in.start(0, 64u);
     uint32_t raw = 0;
     if (mine) {
         const size_t off = offsets ? (size_t)offsets[my] : (size_t)my * stride;
@@ -60,20 +59,22 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
         const size_t sp = off + kHdr;                              // first bitstream byte, any alignment
         wp = reinterpret_cast<const uint32_t *>(payload) + (sp >> 2);
         const uint32_t skip = 8u * (uint32_t)(sp & 3u);
-        in.buf = (uint64_t)bswap32(*clamp_ptr(wp, wend)) << (32u + skip);
-        in.have = 32u - skip;
+        const uint64_t w0 = bswap32(*clamp_ptr(wp, wend));
         ++wp;
-        in.feed(bswap32(*clamp_ptr(wp, wend)));                          // 40..64 bits
+        const uint64_t w1 = bswap32(*clamp_ptr(wp, wend));
         ++wp;
+        in.start(((w0 << 32) | w1) << skip, 64u - skip);           // 40..64 bits
         ahead = *clamp_ptr(wp, wend);
     }
     // initializeDecoder (:582-603): the first 16 bits
     uint32_t code = in.take(16u);
-    if (in.hungry()) {
-        in.feed(bswap32(ahead));
-        ++wp;
-        ahead = *clamp_ptr(wp, wend);
-    }
+    auto refill = [&]() {                                          // predicated, no divergence
+        const bool h = in.hungry();
+        in.feed_if(h, bswap32(ahead));
+        wp += h ? 1 : 0;
+        if (h) ahead = *clamp_ptr(wp, wend);
+    };
+    refill();
     uint32_t L = 0, V = 0;
 
     const uint32_t max_raw = __reduce_max_sync(kFull, raw);
@@ -90,11 +91,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
         uint32_t k, u, U1;
         narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
         code = advance_code(code, k, u, in);
-        if (in.hungry()) {
-            in.feed(bswap32(ahead));
-            ++wp;
-            ahead = *clamp_ptr(wp, wend);
-        }
+        refill();
     };
 
     const uint32_t min_raw = __reduce_min_sync(kFull, mine ? raw : kPacket);

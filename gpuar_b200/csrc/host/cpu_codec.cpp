@@ -42,9 +42,8 @@ std::uint32_t cpuDecodePacket(const std::uint8_t *pkt, std::uint8_t *out)
         return w;
     };
     BitSource in;
-    in.buf = (std::uint64_t)word() << 32;
-    in.have = 32;
-    in.feed(word());
+    const std::uint64_t w0 = word(), w1 = word();
+    in.start((w0 << 32) | w1, 64u);
     std::uint32_t code = in.take(16u);
     if (in.hungry()) in.feed(word());
     std::uint32_t L = 0, V = 0;

@@ -66,11 +66,11 @@ uint32_t host_model_decode_packet(const uint8_t *payload, size_t readable, size_
     const uint32_t *wp = words + (sp >> 2);
     const uint32_t skip = 8u * (uint32_t)(sp & 3u);
     BitSource in;
-    in.buf = (uint64_t)word(wp) << (32u + skip);
-    in.have = 32u - skip;
+    const uint64_t w0 = word(wp);
     ++wp;
-    in.feed(word(wp));
+    const uint64_t w1 = word(wp);
     ++wp;
+    in.start(((w0 << 32) | w1) << skip, 64u - skip);
     uint32_t ahead = word(wp);
     uint32_t code = in.take(16u);
     if (in.hungry()) { in.feed(ahead); ++wp; ahead = word(wp); }
