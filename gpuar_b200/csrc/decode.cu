@@ -26,15 +26,38 @@ __device__ __forceinline__ const uint32_t *clamp_ptr(const uint32_t *p, const ui
     return p < last ? p : last;          // reads past the buffer are pinned to its last word
 }
 
+constexpr uint32_t kRing = 8;        // per-lane ring of stream words in shared memory
+constexpr uint32_t kAhead = 3;       // words requested ahead of the reader
+
+template <bool kRingFeed>
 struct DecShared {
-    uint64_t tree[kTreeStored][32];  // 21504 B; lane l owns column l (banks 2l, 2l+1); root in registers
+    uint64_t tree[kTreeStored][32];          // 21504 B; lane l owns column l (banks 2l, 2l+1); root in registers
+    uint32_t ring[kRingFeed ? kRing : 1][32];  // 1024 B stream ring (ring feed only: 21504 B keeps 10 CTAs per SM)
 };
 
+// 4-byte asynchronous global->shared copy (LDGSTS): no register, no scoreboard -- the stream
+// prefetch never stalls the dependent chain of the decoder.
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gmem_src)
+{
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+// kRingFeed selects how the bit window is refilled:
+//   true   cp.async ring + predicated feed: nothing in the step ever waits on a global load and
+//          there is no divergent branch -- shortest dependent chain; used when the input is at
+//          most one resident wave (each scheduler holds ~1 warp and latency is everything);
+//   false  one word prefetched in a register, fed under a (divergent) branch -- fewer
+//          instructions per step; used when many warps per scheduler hide the latency.
+template <bool kRingFeed>
 __global__ void __launch_bounds__(32)
 decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64_t *__restrict__ offsets,
               uint32_t stride, uint32_t n_packets, uint8_t *__restrict__ out)
 {
-    __shared__ __align__(16) DecShared sm;
+    __shared__ __align__(16) DecShared<kRingFeed> sm;
     const uint32_t lane = lane_id();
     const uint32_t my = blockIdx.x * 32u + lane;
     const bool mine = my < n_packets;
@@ -44,11 +67,12 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     uint64_t root;
     tree_init(root, tree, 32u);
 
-    // bit source: aligned 32-bit words of the packet's bitstream, one word prefetched
+    // bit source: aligned 32-bit words of the packet's bitstream.  The window is fed from a
+    // per-lane ring in shared memory that cp.async keeps kAhead words ahead of the reader.
     const uint32_t *const wend = reinterpret_cast<const uint32_t *>(payload) + (readable >> 2) - 1;  // last readable word
-    const uint32_t *wp = wend;      // word held in `ahead`
-    uint32_t ahead = 0;             // prefetched word, still little-endian: swapped when fed, so that
-                                    // nothing waits on the load until the reservoir needs it
+    const uint32_t *gp = wend;      // next word to request (ring) / word held in `ahead` (register)
+    uint32_t rd = 0, wr = 0;        // ring positions: words consumed / requested
+    uint32_t ahead = 0;             // register feed: prefetched word, byte-swapped only when fed
     BitSource in;
     in.start(0, 64u);
     uint32_t raw = 0;
@@ -57,23 +81,44 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
         const uint32_t hdr = (uint32_t)payload[off + 2] | ((uint32_t)payload[off + 3] << 8);   // rawLen, :859
         raw = min(hdr, kPacket);
         const size_t sp = off + kHdr;                              // first bitstream byte, any alignment
-        wp = reinterpret_cast<const uint32_t *>(payload) + (sp >> 2);
+        gp = reinterpret_cast<const uint32_t *>(payload) + (sp >> 2);
         const uint32_t skip = 8u * (uint32_t)(sp & 3u);
-        const uint64_t w0 = bswap32(*clamp_ptr(wp, wend));
-        ++wp;
-        const uint64_t w1 = bswap32(*clamp_ptr(wp, wend));
-        ++wp;
+        const uint64_t w0 = bswap32(*clamp_ptr(gp, wend));
+        ++gp;
+        const uint64_t w1 = bswap32(*clamp_ptr(gp, wend));
+        ++gp;
         in.start(((w0 << 32) | w1) << skip, 64u - skip);           // 40..64 bits
-        ahead = *clamp_ptr(wp, wend);
     }
+    if (kRingFeed) {
+        for (; wr < kAhead; ++wr, ++gp) cp_async4(&sm.ring[wr][lane], clamp_ptr(gp, wend));
+        cp_async_commit();
+        cp_async_wait<0>();
+    } else {
+        ahead = *clamp_ptr(gp, wend);
+    }
+    auto refill = [&]() {
+        if (kRingFeed) {
+            // One refill per step, predicated, never divergent: feed the ring's next word if the
+            // window has room, and request one more word.  A word is read at least kAhead steps
+            // after it was requested, so waiting for all but the kAhead-1 newest groups makes it
+            // visible.
+            cp_async_wait<kAhead - 1>();
+            const uint32_t w = sm.ring[rd & (kRing - 1u)][lane];
+            const bool h = in.hungry();
+            in.feed_if(h, bswap32(w));
+            if (h) cp_async4(&sm.ring[wr & (kRing - 1u)][lane], clamp_ptr(gp, wend));
+            cp_async_commit();
+            rd += h ? 1u : 0u;
+            wr += h ? 1u : 0u;
+            gp += h ? 1 : 0;
+        } else if (in.hungry()) {
+            in.feed(bswap32(ahead));
+            ++gp;
+            ahead = *clamp_ptr(gp, wend);
+        }
+    };
     // initializeDecoder (:582-603): the first 16 bits
     uint32_t code = in.take(16u);
-    auto refill = [&]() {                                          // predicated, no divergence
-        const bool h = in.hungry();
-        in.feed_if(h, bswap32(ahead));
-        wp += h ? 1 : 0;
-        if (h) ahead = *clamp_ptr(wp, wend);
-    };
     refill();
     uint32_t L = 0, V = 0;
 
@@ -137,7 +182,14 @@ cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint6
                           uint32_t packets, uint8_t *d_out, cudaStream_t st)
 {
     if (!packets) return cudaSuccess;
-    decode_kernel<<<(packets + 31u) / 32u, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t grid = (packets + 31u) / 32u;
+    if (grid <= (uint32_t)sms * 10u)             // at most one resident wave: latency-optimised feed
+        decode_kernel<true><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out);
+    else
+        decode_kernel<false><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out);
     count_launch();
     return cudaGetLastError();
 }
