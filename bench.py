@@ -328,6 +328,8 @@ def run_ours(args):
     barrier()
     t_enc = timed(enc_step, args.steps)
     barrier()
+    t_local = timed(lambda: dev.encode(x, payload, total), args.steps) if world > 1 else t_enc
+    barrier()
     t_dec = timed(dec_step, args.steps)
     barrier()
     spans = _lib.profile_read()
@@ -360,10 +362,10 @@ def run_ours(args):
     gip_bytes = int(g.size)
 
     # ---- max over ranks
-    times = torch.tensor([t_enc, t_dec, t_e2e_enc, t_e2e_dec], dtype=torch.float64, device="cuda")
+    times = torch.tensor([t_enc, t_dec, t_e2e_enc, t_e2e_dec, t_local], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_enc, t_dec, t_e2e_enc, t_e2e_dec = (float(v) for v in times.tolist())
+    t_enc, t_dec, t_e2e_enc, t_e2e_dec, t_local = (float(v) for v in times.tolist())
 
     if rank == 0:
         job = nbytes * world
@@ -380,6 +382,9 @@ def run_ours(args):
                        "payload_bytes_rank0": c, "l2": "flushed between timed iterations (256 MiB write)",
                        "parallelism": f"packet-range shards x{world}" if world > 1 else "single GPU",
                        "encode_path": args.encode_path},
+            "encode_shards_in_place": {"value": job / (t_local / args.steps) / GB, "unit": "GB/s",
+                                       "note": "same encode without the NVLink gather into rank 0 (SURVEY 8e reports both); "
+                                               "`value` includes the gather, which is ingress-limited on rank 0"},
             "decode": {"value": job / (t_dec / args.steps) / GB, "unit": "GB/s",
                        "ms_per_step": t_dec / args.steps * 1e3,
                        "includes": "device packet-chain discovery + decode kernel"},
