@@ -257,3 +257,27 @@ def test_config3_1gib_skewed_round_trip(dev):
     assert [int(v) for v in result.tolist()[:3]] == [packets, n, 0]
     back = dev.decode(payload, c, offsets, packets)
     assert torch.equal(back, x)
+
+
+def test_beyond_4gib_header_and_round_trip(dev, codec):
+    """sizes past 2^32.  The reference's header fields are 32 bit
+    (file_header.hpp:61-72); ours carry the high halves in the bytes the reference leaves undefined."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs ~40 GB of free device memory")
+    n = (4 << 30) + (64 << 20) + 65536 * 3
+    x = D.mixed_device(31, n)
+    payload, total, _ = dev.encode(x)
+    c = int(total.item())
+    assert 0.5 * n < c < 0.7 * n
+    packets = n // 8192
+    offsets, result = dev.index(payload, c, packets)
+    assert [int(v) for v in result.tolist()[:3]] == [packets, n, 0]
+    assert int(offsets[packets - 1].item()) > (1 << 31)
+    back = dev.decode(payload, c, offsets, packets)
+    assert torch.equal(back, x)
+    h = codec.write_header(n, 20 + c)
+    assert int.from_bytes(h[4:12].tobytes(), "little") == n and int.from_bytes(h[4:8].tobytes(), "little") == n % (1 << 32)
+    # prefix property: the first 1 MiB of the payload is the golden payload of mixed(31, 1 MiB)
+    head = O.encode(D.mixed(31, 1 << 20))
+    assert np.array_equal(payload[: head.size].cpu().numpy(), head)
