@@ -15,7 +15,8 @@ Workloads: u64m = uniform(0x64, 64 MiB) (BASELINE config 2, the d
 s1g = and3(2, 1 GiB) (config 3), m2g = mixed(3, 2 GiB per rank) (config 4's per-GPU shard at 8 GPUs).
 With N > 1 (torchrun) every rank encodes its own packet range of the N-times-larger input
 (weak scaling), the ranks' payload totals are exclusive-scanned, and the streams are concatenated
-into rank 0's buffer with peer copies over NVLink.
+with peer stores over NVLink into W equal segments (segment g on GPU g); the gather of the whole
+stream onto one GPU and the no-exchange case are timed beside it.
 
 --impl reference times the reference's own CPU codec (oracle/_ref, compiled from the reference
 sources; falls back to the oracle port) on the host cores.
@@ -257,7 +258,8 @@ def run_ours(args):
             os.close(saved)
     dev = codec.DeviceCodec(local)
     _lib.set_option(_lib.OPT_ENCODE_PATH, {"auto": 0, "fused": 1, "ws": 2}[args.encode_path])
-    sharded = ShardedCodec(dev, rank, world)
+    sharded = ShardedCodec(dev, rank, world, "segments")
+    gathered = ShardedCodec(dev, rank, world, "gather") if world > 1 else None
 
     gen, seed, nbytes, desc = WORKLOADS[args.workload]
     # weak scaling: the job is `world` times the per-rank workload; rank r owns packets [r*P, (r+1)*P)
@@ -277,6 +279,8 @@ def run_ours(args):
     out = torch.empty(packets * 8192, dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
     sharded.reserve(cap)
+    if gathered:
+        gathered.reserve(cap)
 
     def enc_step():
         dev.encode(x, payload, total)
@@ -330,6 +334,18 @@ def run_ours(args):
     barrier()
     t_local = timed(lambda: dev.encode(x, payload, total), args.steps) if world > 1 else t_enc
     barrier()
+
+    def gather_step():
+        dev.encode(x, payload, total)
+        gathered.concat(payload, total)
+
+    t_gather = t_enc
+    if gathered:
+        for _ in range(3):
+            gather_step()
+        barrier()
+        t_gather = timed(gather_step, args.steps)
+        barrier()
     t_dec = timed(dec_step, args.steps)
     barrier()
     spans = _lib.profile_read()
@@ -362,10 +378,10 @@ def run_ours(args):
     gip_bytes = int(g.size)
 
     # ---- max over ranks
-    times = torch.tensor([t_enc, t_dec, t_e2e_enc, t_e2e_dec, t_local], dtype=torch.float64, device="cuda")
+    times = torch.tensor([t_enc, t_dec, t_e2e_enc, t_e2e_dec, t_local, t_gather], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_enc, t_dec, t_e2e_enc, t_e2e_dec, t_local = (float(v) for v in times.tolist())
+    t_enc, t_dec, t_e2e_enc, t_e2e_dec, t_local, t_gather = (float(v) for v in times.tolist())
 
     if rank == 0:
         job = nbytes * world
@@ -383,8 +399,11 @@ def run_ours(args):
                        "parallelism": f"packet-range shards x{world}" if world > 1 else "single GPU",
                        "encode_path": args.encode_path},
             "encode_shards_in_place": {"value": job / (t_local / args.steps) / GB, "unit": "GB/s",
-                                       "note": "same encode without the NVLink gather into rank 0 (SURVEY 8e reports both); "
-                                               "`value` includes the gather, which is ingress-limited on rank 0"},
+                                       "note": "encode only, every shard's payload left on its own GPU (SURVEY 8e)"},
+            "encode_gather_one_gpu": {"value": job / (t_gather / args.steps) / GB, "unit": "GB/s",
+                                      "note": "concatenation of the whole stream into rank 0's memory: ingress-limited "
+                                              "on that GPU (SURVEY 8e); `value` concatenates into W equal segments, "
+                                              "segment g on GPU g, so every GPU receives total/W bytes"},
             "decode": {"value": job / (t_dec / args.steps) / GB, "unit": "GB/s",
                        "ms_per_step": t_dec / args.steps * 1e3,
                        "includes": "device packet-chain discovery + decode kernel"},

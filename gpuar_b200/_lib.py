@@ -47,7 +47,7 @@ SIGNATURES = {
     "gpuar_b200_write_header": (None, [_vp, C.c_uint64, C.c_uint64]),
     "gpuar_b200_check_header": (C.c_int, [_vp]),
     "gpuar_b200_peer_concat": (C.c_int, [_vp, C.c_int, _sz, _vp, C.c_int, _sz, _vp]),
-    "gpuar_b200_shard_concat": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _sz, _vp]),
+    "gpuar_b200_shard_concat": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp), C.c_int, _sz, _vp, _vp]),
     "gpuar_b200_device_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
     "gpuar_b200_device_free": (C.c_int, [_vp]),
     "gpuar_b200_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),

@@ -418,11 +418,15 @@ int gpuar_b200_peer_concat(uint8_t *d_dst, int dst_device, size_t dst_offset, co
 }
 
 int gpuar_b200_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, int rank, int world,
-                            uint8_t *d_gather, size_t gather_cap, void *stream)
+                            uint8_t *const *segments, int n_segments, size_t seg_cap, uint64_t *d_layout, void *stream)
 {
-    if (!d_payload || !d_totals || !d_gather || rank < 0 || rank >= world) return GPUAR_E_ARG;
+    if (!d_payload || !d_totals || !segments || rank < 0 || rank >= world || world > 16) return GPUAR_E_ARG;
+    if (n_segments < 1 || n_segments > 16) return GPUAR_E_ARG;
     if ((uintptr_t)d_payload & 15u) return GPUAR_E_ARG;
-    return ck(launch_shard_concat(d_payload, d_totals, (uint32_t)rank, d_gather, gather_cap, (cudaStream_t)stream));
+    for (int g = 0; g < n_segments; ++g)
+        if (!segments[g]) return GPUAR_E_ARG;
+    return ck(launch_shard_concat(d_payload, d_totals, (uint32_t)rank, (uint32_t)world, segments, (uint32_t)n_segments,
+                                  seg_cap, d_layout, (cudaStream_t)stream));
 }
 
 int gpuar_b200_device_alloc(size_t bytes, void **d_ptr)

@@ -184,6 +184,27 @@ __device__ __forceinline__ void warp_copy_unaligned(uint8_t *__restrict__ dst, c
     if (lane < len - done) dst[done + lane] = src[done + lane];
 }
 
+// same, but the source may have any alignment too (pieces split at segment boundaries)
+__device__ __forceinline__ void warp_copy_any(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
+                                              uint32_t len, uint32_t lane)
+{
+    if ((((uintptr_t)src) & 15u) == 0) {
+        warp_copy_unaligned(dst, src, len, lane);
+    } else if (((((uintptr_t)src) ^ ((uintptr_t)dst)) & 3u) == 0) {
+        // same phase modulo 4: byte head, 4-byte body, byte tail
+        const uint32_t head = min(len, (uint32_t)((4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u));
+        if (lane < head) dst[lane] = src[lane];
+        const uint32_t body = (len - head) >> 2;
+        const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src + head);
+        uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
+        for (uint32_t c = lane; c < body; c += 32u) d4[c] = s4[c];
+        const uint32_t done = head + (body << 2);
+        if (lane < len - done) dst[done + lane] = src[done + lane];
+    } else {
+        for (uint32_t c = lane; c < len; c += 32u) dst[c] = src[c];
+    }
+}
+
 __global__ void __launch_bounds__(kCompactThreads)
 compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const uint32_t *__restrict__ sizes,
                uint32_t n_packets, uint8_t *__restrict__ payload, uint64_t *__restrict__ desc,
@@ -233,27 +254,56 @@ compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const ui
 }
 
 // ------------------------------------------------- multi-GPU stream concatenation
-// Rank r's compacted payload lands at the exclusive scan of the ranks' totals inside the
-// gathered payload, which may live on another GPU of the box: `gather` is then a
-// peer-mapped pointer (cudaIpcOpenMemHandle) and the 16-byte stores below travel over
-// NVLink.  The totals are read from device memory, so the host never waits for a size.
+// The ranks' payloads are concatenated in rank (= packet) order: rank r's stream starts at the
+// exclusive scan of the W payload totals.  The concatenated stream lives in W equal SEGMENTS of
+// S = ceil(total / W) bytes (rounded up to 256), segment g on GPU g: global offset o is byte
+// o % S of segment o / S.  With balanced shards almost every byte stays on its own GPU and only
+// the spill-over crosses NVLink; with skewed shards every GPU still receives exactly S bytes, so
+// no GPU's ingress is the bottleneck (gathering everything onto one GPU is ingress-limited to
+// one link set).  `segments` holds the device pointers, local or peer-mapped (cudaIpcOpenMemHandle);
+// a single segment of the whole capacity reproduces the gather-to-one-GPU layout.  The totals
+// are read from device memory, so the host never waits for a size; stores are 16 bytes wide.
 constexpr uint32_t kConcatThreads = 256;
 constexpr uint32_t kConcatPiece = 4096;             // bytes per warp-iteration (16-byte aligned source)
 
+struct SegmentList { uint8_t *base[16]; };
+
 __global__ void __launch_bounds__(kConcatThreads)
 shard_concat_kernel(const uint8_t *__restrict__ payload, const uint64_t *__restrict__ totals, uint32_t rank,
-                    uint8_t *__restrict__ gather, uint64_t gather_cap)
+                    uint32_t world, SegmentList segments, uint32_t n_segments, uint64_t seg_cap,
+                    uint64_t *__restrict__ layout_out)
 {
-    uint64_t base = 0;
-    for (uint32_t r = 0; r < rank; ++r) base += totals[r];
+    uint64_t base = 0, all = 0;
+    for (uint32_t r = 0; r < world; ++r) {
+        const uint64_t t = totals[r];
+        if (r < rank) base += t;
+        all += t;
+    }
     const uint64_t bytes = totals[rank];
-    if (base + bytes > gather_cap) return;           // never write past the destination
+    // segment size: equal split of the whole stream, 256-byte granules; one segment = plain gather
+    uint64_t seg = n_segments > 1 ? (((all + n_segments - 1) / n_segments + 255) & ~(uint64_t)255) : seg_cap;
+    if (seg == 0) seg = 256;
+    if (seg > seg_cap) return;                       // never write past a destination (caller sized it too small)
+    if (layout_out && blockIdx.x == 0 && threadIdx.x == 0) {
+        layout_out[0] = all;
+        layout_out[1] = seg;
+        layout_out[2] = base;
+    }
     const uint32_t lane = lane_id();
     const uint64_t warps = (uint64_t)gridDim.x * (kConcatThreads / 32u);
     const uint64_t w = (uint64_t)blockIdx.x * (kConcatThreads / 32u) + (threadIdx.x >> 5);
     for (uint64_t at = w * kConcatPiece; at < bytes; at += warps * kConcatPiece) {
-        const uint32_t len = (uint32_t)min((uint64_t)kConcatPiece, bytes - at);
-        warp_copy_unaligned(gather + base + at, payload + at, len, lane);
+        uint32_t len = (uint32_t)min((uint64_t)kConcatPiece, bytes - at);
+        uint64_t o = base + at;                      // global offset of this piece
+        const uint8_t *src = payload + at;
+        while (len) {                                // a piece may straddle a segment boundary
+            const uint64_t g = o / seg, in = o - g * seg;
+            const uint32_t part = (uint32_t)min((uint64_t)len, seg - in);
+            if (g < n_segments) warp_copy_any(segments.base[g] + in, src, part, lane);
+            o += part;
+            src += part;
+            len -= part;
+        }
     }
 }
 
@@ -291,13 +341,18 @@ cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const u
     return cudaGetLastError();
 }
 
-cudaError_t launch_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, uint32_t rank, uint8_t *d_gather,
-                                uint64_t gather_cap, cudaStream_t st)
+cudaError_t launch_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, uint32_t rank, uint32_t world,
+                                uint8_t *const *segments, uint32_t n_segments, uint64_t seg_cap, uint64_t *d_layout,
+                                cudaStream_t st)
 {
+    if (n_segments == 0 || n_segments > 16 || world > 16) return cudaErrorInvalidValue;
+    SegmentList list{};
+    for (uint32_t g = 0; g < n_segments; ++g) list.base[g] = segments[g];
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    shard_concat_kernel<<<(unsigned)sms * 4u, kConcatThreads, 0, st>>>(d_payload, d_totals, rank, d_gather, gather_cap);
+    shard_concat_kernel<<<(unsigned)sms * 4u, kConcatThreads, 0, st>>>(d_payload, d_totals, rank, world, list,
+                                                                        n_segments, seg_cap, d_layout);
     count_launch();
     return cudaGetLastError();
 }

@@ -18,8 +18,9 @@ cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const u
                            uint32_t packets, uint8_t *d_payload, uint64_t *d_desc, uint64_t *d_total,
                            cudaStream_t st);
 
-cudaError_t launch_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, uint32_t rank, uint8_t *d_gather,
-                                uint64_t gather_cap, cudaStream_t st);
+cudaError_t launch_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, uint32_t rank, uint32_t world,
+                                uint8_t *const *segments, uint32_t n_segments, uint64_t seg_cap, uint64_t *d_layout,
+                                cudaStream_t st);
 
 // decode.cu: d_offsets == nullptr means packet p starts at p * stride (reference slot layout)
 cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint64_t *d_offsets, uint32_t stride,

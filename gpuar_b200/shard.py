@@ -33,18 +33,20 @@ def exclusive_scan(totals) -> list[int]:
 class ShardedCodec:
     """Per-rank handle.  world == 1: nothing to exchange."""
 
-    def __init__(self, dev, rank: int, world: int):
+    def __init__(self, dev, rank: int, world: int, layout: str = "segments"):
+        """layout: "segments" = the concatenated stream in `world` equal segments, segment g on GPU g
+        (every GPU receives the same number of bytes); "gather" = the whole stream on rank 0."""
         self.dev, self.rank, self.world = dev, rank, world
         self._peer = None
         if world > 1:
             from ._peer import PeerConcat
-            self._peer = PeerConcat(rank, world)
+            self._peer = PeerConcat(rank, world, layout)
 
     def reserve(self, cap_per_rank: int) -> None:
         if self._peer:
             self._peer.reserve(cap_per_rank)
 
     def concat(self, payload, total) -> None:
-        """Land this rank's payload[:total] at its scanned offset in rank 0's gathered buffer."""
+        """Land this rank's payload[:total] at its scanned offset in the concatenated stream."""
         if self._peer:
             self._peer.concat(payload, total)

@@ -119,10 +119,16 @@ int gpuar_b200_peer_concat(uint8_t *d_dst, int dst_device, size_t dst_offset, co
                            int src_device, size_t bytes, void *stream);
 /* The same without a host round trip (what bench.py --gpus N uses): one kernel per rank reads
  * the W payload totals from device memory (d_totals[world], e.g. all-gathered), takes its
- * exclusive scan at `rank` as the landing offset and stores d_payload[0..totals[rank]) into
- * d_gather -- a local or peer-mapped (IPC) pointer -- with 16-byte stores over NVLink. */
+ * exclusive scan at `rank` as the landing offset and stores d_payload[0..totals[rank]) into the
+ * concatenated stream with 16-byte stores over NVLink.  The stream is laid out in n_segments
+ * equal segments of S = ceil(total / n_segments) bytes (rounded up to 256): global offset o is
+ * byte o % S of segments[o / S]; segments[] are host-array device pointers, local or peer-mapped
+ * (IPC), each with capacity seg_cap.  n_segments = world with segment g on GPU g keeps every
+ * GPU's ingress at S bytes; n_segments = 1 gathers the whole stream into one buffer (then S =
+ * seg_cap).  d_layout (optional, device u64[3]) receives total, S and this rank's base offset. */
 int gpuar_b200_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, int rank, int world,
-                            uint8_t *d_gather, size_t gather_cap, void *stream);
+                            uint8_t *const *segments, int n_segments, size_t seg_cap, uint64_t *d_layout,
+                            void *stream);
 /* plain cudaMalloc/cudaFree on the current device: IPC-exportable allocations for the gather buffer */
 int gpuar_b200_device_alloc(size_t bytes, void **d_ptr);
 int gpuar_b200_device_free(void *d_ptr);

@@ -30,35 +30,55 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = codec.DeviceCodec(local)
-    sh = ShardedCodec(dev, rank, world)
     ok = True
-    for n in (8192 * 64 * world + 4321, 8192 * 3, 12 << 20):
-        data = D.mixed(17, n)
-        b0, b1 = byte_range(n, rank, world)
-        x = torch.from_numpy(data[b0:b1].copy()).cuda()
-        cap = codec.payload_bound(max(b1 - b0, 8192))
-        sh.reserve(codec.payload_bound(n))
-        payload, total, _ = dev.encode(x) if b1 > b0 else (torch.zeros(cap + 16, dtype=torch.uint8, device="cuda"),
-                                                           torch.zeros(1, dtype=torch.int64, device="cuda"), None)
-        sh.concat(payload, total)
-        torch.cuda.synchronize()
-        dist.barrier()
-        if rank == 0:
-            want = O.ref_encode(data, 8) if O.have_ref() else O.encode(data)
-            totals = sh._peer.totals.cpu().numpy()
-            got = sh._peer.gathered(int(totals.sum())).cpu().numpy()
-            same = got.size == want.size and np.array_equal(got, want)
-            back = dev.decode_bytes(torch.from_numpy(got).cuda()).cpu().numpy() if same else np.zeros(0, np.uint8)
-            rt = np.array_equal(back, data)
-            print(f"n={n} world={world} totals={totals.tolist()} gathered==single-GPU payload: {same}; round trip: {rt}",
-                  flush=True)
-            ok = ok and same and rt
-        dist.barrier()
+    for layout in ("segments", "gather"):
+        sh = ShardedCodec(dev, rank, world, layout)
+        for n in (8192 * 64 * world + 4321, 8192 * 3, 12 << 20):
+            data = D.mixed(17, n)
+            b0, b1 = byte_range(n, rank, world)
+            x = torch.from_numpy(data[b0:b1].copy()).cuda()
+            cap = codec.payload_bound(max(b1 - b0, 8192))
+            sh.reserve(codec.payload_bound(n))
+            payload, total, _ = dev.encode(x) if b1 > b0 else (torch.zeros(cap + 16, dtype=torch.uint8, device="cuda"),
+                                                               torch.zeros(1, dtype=torch.int64, device="cuda"), None)
+            sh.concat(payload, total)
+            torch.cuda.synchronize()
+            dist.barrier()
+            # every owner hands its segment to rank 0 (gloo-style gather through NCCL, test only)
+            seg, valid = sh._peer.my_segment()
+            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(sizes, torch.tensor([valid], dtype=torch.int64, device="cuda"))
+            sizes = [int(v.item()) for v in sizes]
+            pieces = []
+            for g in range(world):
+                if sizes[g] == 0:
+                    continue
+                if g == 0:
+                    if rank == 0:
+                        pieces.append(seg.clone())
+                elif rank == g:
+                    dist.send(seg.contiguous(), dst=0)
+                elif rank == 0:
+                    buf = torch.empty(sizes[g], dtype=torch.uint8, device="cuda")
+                    dist.recv(buf, src=g)
+                    pieces.append(buf)
+            if rank == 0:
+                want = O.ref_encode(data, 8) if O.have_ref() else O.encode(data)
+                got = torch.cat(pieces).cpu().numpy() if pieces else np.zeros(0, np.uint8)
+                same = got.size == want.size and np.array_equal(got, want)
+                back = dev.decode_bytes(torch.from_numpy(got).cuda()).cpu().numpy() if same else np.zeros(0, np.uint8)
+                rt = np.array_equal(back, data)
+                print(f"layout={layout} n={n} world={world} segment bytes={sizes} concatenated==single-GPU payload: "
+                      f"{same}; round trip: {rt}", flush=True)
+                ok = ok and same and rt
+            dist.barrier()
+        sh._peer.release()
     if rank == 0:
         print("MULTIGPU PARITY OK" if ok else "MULTIGPU PARITY FAILED", flush=True)
-    sh._peer.release()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
     dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    sys.exit(0 if int(flag.item()) else 1)
 
 
 if __name__ == "__main__":
