@@ -270,27 +270,28 @@ def run_ours(args):
         x = D.and3_device(seed, nbytes, start)
     else:
         x = D.mixed_device(seed, nbytes, start)
-    packets = nbytes // 8192
-    cap = codec.payload_bound(nbytes)
+    packet = args.packet
+    packets = (nbytes + packet - 1) // packet
+    cap = codec.payload_bound(nbytes, packet)
     payload = torch.empty(cap + 16, dtype=torch.uint8, device="cuda")
     total = torch.zeros(1, dtype=torch.int64, device="cuda")
     offsets = torch.empty(packets + 1, dtype=torch.int64, device="cuda")
     result = torch.zeros(4, dtype=torch.int64, device="cuda")
-    out = torch.empty(packets * 8192, dtype=torch.uint8, device="cuda")
+    out = torch.empty(packets * packet, dtype=torch.uint8, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
     sharded.reserve(cap)
     if gathered:
         gathered.reserve(cap)
 
     def enc_step():
-        dev.encode(x, payload, total)
+        dev.encode(x, payload, total, packet=packet)
         sharded.concat(payload, total)            # N > 1: totals scan + NVLink peer copies; N = 1: nothing
 
     c_holder = [0]
 
     def dec_step():
-        dev.index(payload, c_holder[0], packets, offsets, result)
-        dev.decode(payload, c_holder[0], offsets, packets, out)
+        dev.index(payload, c_holder[0], packets, offsets, result, packet=packet)
+        dev.decode(payload, c_holder[0], offsets, packets, out, packet=packet)
 
     def barrier():
         torch.cuda.synchronize()
@@ -321,7 +322,7 @@ def run_ours(args):
         dec_step()
     torch.cuda.synchronize()
     assert [int(v) for v in result.tolist()[:3]] == [packets, nbytes, 0], result.tolist()
-    assert torch.equal(out, x), "decode(encode(x)) != x"
+    assert torch.equal(out[:nbytes], x), "decode(encode(x)) != x"
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -332,11 +333,11 @@ def run_ours(args):
     barrier()
     t_enc = timed(enc_step, args.steps)
     barrier()
-    t_local = timed(lambda: dev.encode(x, payload, total), args.steps) if world > 1 else t_enc
+    t_local = timed(lambda: dev.encode(x, payload, total, packet=packet), args.steps) if world > 1 else t_enc
     barrier()
 
     def gather_step():
-        dev.encode(x, payload, total)
+        dev.encode(x, payload, total, packet=packet)
         gathered.concat(payload, total)
 
     t_gather = t_enc
@@ -356,7 +357,7 @@ def run_ours(args):
     # ---- e2e through the host-buffer entry points, pinned host memory
     host_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     host_in.copy_(x)
-    host_gip = torch.empty(20 + cap, dtype=torch.uint8).pin_memory()
+    host_gip = torch.empty(20 + codec.payload_bound(nbytes), dtype=torch.uint8).pin_memory()   # e2e: 8192-byte packets
     host_out = torch.empty(nbytes + 8192, dtype=torch.uint8).pin_memory()
     np_in, np_gip, np_out = host_in.numpy(), host_gip.numpy(), host_out.numpy()
     e2e_steps = max(1, min(args.steps, 5))
@@ -394,7 +395,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": t_enc / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": desc, "bytes_per_rank": nbytes, "packet_bytes": 8192,
+            "config": {"workload": args.workload, "desc": desc, "bytes_per_rank": nbytes, "packet_bytes": packet,
                        "payload_bytes_rank0": c, "l2": "flushed between timed iterations (256 MiB write)",
                        "parallelism": f"packet-range shards x{world}" if world > 1 else "single GPU",
                        "encode_path": args.encode_path},
@@ -443,6 +444,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="u64m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--packet", type=int, default=8192,
+                    help="raw bytes per packet for the device-resident numbers (8192 = the reference format; "
+                         "4096/12288/16112 for the BASELINE config-5 sweep; e2e and CPU baseline stay at 8192)")
     ap.add_argument("--encode-path", default="auto", choices=["auto", "fused", "ws"],
                     help="encoder kernel: auto (by packet count), fused lane=packet, warp-specialised")
     args = ap.parse_args()

@@ -41,6 +41,11 @@ SIGNATURES = {
     "gpuar_b200_encode": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     "gpuar_b200_index": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _vp, _sz, _vp]),
     "gpuar_b200_decode": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _sz, _vp]),
+    "gpuar_b200_payload_bound_ex": (_sz, [_sz, _sz]),
+    "gpuar_b200_encode_scratch_bytes_ex": (_sz, [_sz, _sz]),
+    "gpuar_b200_encode_ex": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
+    "gpuar_b200_index_ex": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _sz, _vp]),
+    "gpuar_b200_decode_ex": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp, _sz, _vp]),
     "gpuar_b200_compress_host": (C.c_int, [_vp, _sz, _vp, _sz, C.POINTER(_sz)]),
     "gpuar_b200_decompress_host": (C.c_int, [_vp, _sz, _vp, _sz, C.POINTER(_sz)]),
     "gpuar_b200_gip_raw_size": (C.c_int, [_vp, _sz, C.POINTER(C.c_uint64)]),

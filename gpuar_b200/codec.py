@@ -40,8 +40,8 @@ def packets_of(n: int) -> int:
     return (n + PACKET - 1) // PACKET
 
 
-def payload_bound(n: int) -> int:
-    return int(lib().gpuar_b200_payload_bound(n))
+def payload_bound(n: int, packet: int = PACKET) -> int:
+    return int(lib().gpuar_b200_payload_bound_ex(n, packet))
 
 
 def _stream() -> int:
@@ -66,27 +66,28 @@ class DeviceCodec:
 
     # ------------------------------------------------------------------ encode
     def encode(self, x: torch.Tensor, payload: torch.Tensor | None = None, total: torch.Tensor | None = None,
-               sizes: torch.Tensor | None = None):
+               sizes: torch.Tensor | None = None, packet: int = PACKET):
         """x: uint8 CUDA tensor.  Returns (payload buffer, total[1] int64 on device, sizes or None).
 
-        The payload occupies payload[:total]; nothing is synchronised."""
+        The payload occupies payload[:total]; nothing is synchronised.  `packet` = raw bytes per
+        packet (8192 = the reference format; other multiples of 16 up to 16112 for sweeps)."""
         assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous()
         n = x.numel()
-        cap = payload_bound(n)
+        cap = payload_bound(n, packet)
         if payload is None:
             payload = torch.empty(cap + 16, dtype=torch.uint8, device=x.device)
         if total is None:
             total = torch.zeros(1, dtype=torch.int64, device=x.device)
-        scratch = self._buf("_scratch", int(lib().gpuar_b200_encode_scratch_bytes(n)))
+        scratch = self._buf("_scratch", int(lib().gpuar_b200_encode_scratch_bytes_ex(n, packet)))
         with torch.cuda.device(self.device):
-            check(lib().gpuar_b200_encode(x.data_ptr(), n, payload.data_ptr(), payload.numel(), total.data_ptr(),
-                                          sizes.data_ptr() if sizes is not None else None,
-                                          scratch.data_ptr(), scratch.numel(), _stream()), "gpuar_b200_encode")
+            check(lib().gpuar_b200_encode_ex(x.data_ptr(), n, packet, payload.data_ptr(), payload.numel(),
+                                             total.data_ptr(), sizes.data_ptr() if sizes is not None else None,
+                                             scratch.data_ptr(), scratch.numel(), _stream()), "gpuar_b200_encode_ex")
         return payload, total, sizes
 
     # ------------------------------------------------------------------- index
     def index(self, payload: torch.Tensor, c: int, max_packets: int, offsets: torch.Tensor | None = None,
-              result: torch.Tensor | None = None):
+              result: torch.Tensor | None = None, packet: int = PACKET):
         """Packet offsets of payload[:c] (payload readable PAD bytes past c).
 
         Returns (offsets int64[max_packets], result int64[4] = packets, raw bytes, status, candidates)."""
@@ -97,37 +98,38 @@ class DeviceCodec:
             result = torch.zeros(4, dtype=torch.int64, device=payload.device)
         scratch = self._buf("_iscratch", int(lib().gpuar_b200_index_scratch_bytes(c)))
         with torch.cuda.device(self.device):
-            check(lib().gpuar_b200_index(payload.data_ptr(), c, offsets.data_ptr(), max_packets, result.data_ptr(),
-                                         scratch.data_ptr(), scratch.numel(), _stream()), "gpuar_b200_index")
+            check(lib().gpuar_b200_index_ex(payload.data_ptr(), c, packet, offsets.data_ptr(), max_packets,
+                                            result.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream()),
+                  "gpuar_b200_index_ex")
         return offsets, result
 
     # ------------------------------------------------------------------ decode
     def decode(self, payload: torch.Tensor, c: int, offsets: torch.Tensor, n_packets: int,
-               out: torch.Tensor | None = None) -> torch.Tensor:
-        """Decode n_packets packets; packet p lands at out[p*8192:]."""
+               out: torch.Tensor | None = None, packet: int = PACKET) -> torch.Tensor:
+        """Decode n_packets packets; packet p lands at out[p*packet:]."""
         if out is None:
-            out = torch.empty(max(1, n_packets) * PACKET, dtype=torch.uint8, device=payload.device)
+            out = torch.empty(max(1, n_packets) * packet, dtype=torch.uint8, device=payload.device)
         with torch.cuda.device(self.device):
-            check(lib().gpuar_b200_decode(payload.data_ptr(), c, offsets.data_ptr(), n_packets, out.data_ptr(),
-                                          out.numel(), _stream()), "gpuar_b200_decode")
+            check(lib().gpuar_b200_decode_ex(payload.data_ptr(), c, packet, offsets.data_ptr(), n_packets,
+                                             out.data_ptr(), out.numel(), _stream()), "gpuar_b200_decode_ex")
         return out
 
     # -------------------------------------------------- convenience (synchronises)
-    def encode_bytes(self, x: torch.Tensor) -> torch.Tensor:
-        payload, total, _ = self.encode(x)
+    def encode_bytes(self, x: torch.Tensor, packet: int = PACKET) -> torch.Tensor:
+        payload, total, _ = self.encode(x, packet=packet)
         return payload[: int(total.item())]
 
-    def decode_bytes(self, payload: torch.Tensor) -> torch.Tensor:
+    def decode_bytes(self, payload: torch.Tensor, packet: int = PACKET) -> torch.Tensor:
         """payload: exact-length uint8 CUDA tensor (any capacity); discovers the chain, decodes."""
         c = payload.numel()
         padded = torch.zeros(c + PAD + 16, dtype=torch.uint8, device=payload.device)
         padded[:c] = payload
         max_packets = c // 5 + 1
-        offsets, result = self.index(padded, c, max_packets)
+        offsets, result = self.index(padded, c, max_packets, packet=packet)
         packets, raw, status, _ = (int(v) for v in result.tolist())
         if status != 0:
             raise GpuarError(status, "gpuar_b200_index")
-        out = self.decode(padded, c, offsets, packets)
+        out = self.decode(padded, c, offsets, packets, packet=packet)
         return out[:raw]
 
 

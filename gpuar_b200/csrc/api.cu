@@ -15,19 +15,20 @@ static std::atomic<uint64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-static inline size_t packets_of(size_t n) { return (n + kPacket - 1) / kPacket; }
+static inline size_t packets_of(size_t n, size_t packet = kPacket) { return (n + packet - 1) / packet; }
+static inline bool packet_ok(size_t packet) { return packet >= 16 && packet <= 16112 && packet % 16 == 0; }
 
 // encode scratch: [slots: packets*8704 + 64][sizes: packets*4][descriptors][pad]
 struct EncodePlan {
     size_t packets, off_slots, off_sizes, off_desc, total;
 };
-static EncodePlan encode_plan(size_t n)
+static EncodePlan encode_plan(size_t n, size_t packet = kPacket)
 {
     EncodePlan p{};
-    p.packets = packets_of(n);
+    p.packets = packets_of(n, packet);
     size_t o = 0;
     p.off_slots = o;
-    o += align_up(p.packets * (size_t)kSlot + 64, 256);
+    o += align_up(p.packets * (packet + 512) + 64, 256);
     p.off_sizes = o;
     o += align_up(p.packets * 4 + 4, 256);
     p.off_desc = o;
@@ -44,12 +45,12 @@ static int g_encode_path = 0;                    // 0 auto, 1 fused lane=packet,
 static size_t g_ws_max_packets = (size_t)148 * 5 * 32;
 
 static cudaError_t encode_slots(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t stride, uint32_t *d_sizes,
-                                cudaStream_t st)
+                                uint32_t packet, cudaStream_t st)
 {
-    const size_t packets = packets_of(n);
+    const size_t packets = packets_of(n, packet);
     const bool ws = g_encode_path == 2 || (g_encode_path == 0 && packets <= g_ws_max_packets);
-    return ws ? launch_encode_slots_ws(d_in, n, d_slots, stride, d_sizes, st)
-              : launch_encode_slots(d_in, n, d_slots, stride, d_sizes, st);
+    return ws ? launch_encode_slots_ws(d_in, n, d_slots, stride, d_sizes, packet, st)
+              : launch_encode_slots(d_in, n, d_slots, stride, d_sizes, packet, st);
 }
 
 // ---- optional per-kernel timing (bench.py's roofline): CUDA events recorded on the
@@ -170,14 +171,25 @@ size_t gpuar_b200_encode_scratch_bytes(size_t n) { return encode_plan(n).total; 
 size_t gpuar_b200_index_scratch_bytes(size_t c) { return index_scratch_bytes(c); }
 uint64_t gpuar_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int gpuar_b200_encode(const uint8_t *d_in, size_t n, uint8_t *d_payload, size_t payload_cap,
-                      uint64_t *d_payload_bytes, uint32_t *d_packet_sizes, void *d_scratch,
-                      size_t scratch_bytes, void *stream)
+size_t gpuar_b200_payload_bound_ex(size_t n, size_t packet_bytes)
 {
-    const EncodePlan p = encode_plan(n);
+    return packet_ok(packet_bytes) ? packets_of(n, packet_bytes) * (packet_bytes + 512) + GPUAR_PAD_BYTES : 0;
+}
+size_t gpuar_b200_encode_scratch_bytes_ex(size_t n, size_t packet_bytes)
+{
+    return packet_ok(packet_bytes) ? encode_plan(n, packet_bytes).total : 0;
+}
+
+int gpuar_b200_encode_ex(const uint8_t *d_in, size_t n, size_t packet_bytes, uint8_t *d_payload, size_t payload_cap,
+                         uint64_t *d_payload_bytes, uint32_t *d_packet_sizes, void *d_scratch, size_t scratch_bytes,
+                         void *stream)
+{
+    if (!packet_ok(packet_bytes)) return GPUAR_E_ARG;
+    const EncodePlan p = encode_plan(n, packet_bytes);
+    const uint32_t slot = (uint32_t)packet_bytes + 512u;
     if (!d_payload_bytes || (n && (!d_in || !d_payload || !d_scratch))) return GPUAR_E_ARG;
     if (((uintptr_t)d_in | (uintptr_t)d_payload | (uintptr_t)d_scratch) & 15u) return GPUAR_E_ARG;
-    if (payload_cap < gpuar_b200_payload_bound(n) || scratch_bytes < p.total) return GPUAR_E_ARG;
+    if (payload_cap < gpuar_b200_payload_bound_ex(n, packet_bytes) || scratch_bytes < p.total) return GPUAR_E_ARG;
     if (p.packets > 0xFFFFFFF0ull) return GPUAR_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t *s = static_cast<uint8_t *>(d_scratch);
@@ -185,38 +197,60 @@ int gpuar_b200_encode(const uint8_t *d_in, size_t n, uint8_t *d_payload, size_t 
     cudaError_t e;
     {
         Scope t(GPUAR_SPAN_ENCODE, st);
-        e = encode_slots(d_in, n, s + p.off_slots, kSlot, sizes, st);
+        e = encode_slots(d_in, n, s + p.off_slots, slot, sizes, (uint32_t)packet_bytes, st);
     }
     if (e != cudaSuccess) return ck(e);
     {
         Scope t(GPUAR_SPAN_COMPACT, st);
-        e = launch_compact(s + p.off_slots, kSlot, sizes, (uint32_t)p.packets, d_payload,
+        e = launch_compact(s + p.off_slots, slot, sizes, (uint32_t)p.packets, d_payload,
                            reinterpret_cast<uint64_t *>(s + p.off_desc), d_payload_bytes, st);
     }
     return ck(e);
 }
 
-int gpuar_b200_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets, size_t max_packets,
-                     uint64_t *d_result, void *d_scratch, size_t scratch_bytes, void *stream)
+int gpuar_b200_encode(const uint8_t *d_in, size_t n, uint8_t *d_payload, size_t payload_cap,
+                      uint64_t *d_payload_bytes, uint32_t *d_packet_sizes, void *d_scratch,
+                      size_t scratch_bytes, void *stream)
 {
+    return gpuar_b200_encode_ex(d_in, n, kPacket, d_payload, payload_cap, d_payload_bytes, d_packet_sizes, d_scratch,
+                                scratch_bytes, stream);
+}
+
+int gpuar_b200_index_ex(const uint8_t *d_payload, size_t c, size_t packet_bytes, uint64_t *d_offsets,
+                        size_t max_packets, uint64_t *d_result, void *d_scratch, size_t scratch_bytes, void *stream)
+{
+    if (!packet_ok(packet_bytes)) return GPUAR_E_ARG;
     if (!d_result || !d_scratch || (c && (!d_payload || !d_offsets))) return GPUAR_E_ARG;
     if (((uintptr_t)d_payload | (uintptr_t)d_scratch) & 15u) return GPUAR_E_ARG;
     if (scratch_bytes < index_scratch_bytes(c)) return GPUAR_E_ARG;
     Scope t(GPUAR_SPAN_INDEX, (cudaStream_t)stream);
     return ck(launch_index(d_payload, c, d_offsets, max_packets, d_result, d_scratch, scratch_bytes,
-                           (cudaStream_t)stream));
+                           (uint32_t)packet_bytes, (cudaStream_t)stream));
+}
+
+int gpuar_b200_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets, size_t max_packets,
+                     uint64_t *d_result, void *d_scratch, size_t scratch_bytes, void *stream)
+{
+    return gpuar_b200_index_ex(d_payload, c, kPacket, d_offsets, max_packets, d_result, d_scratch, scratch_bytes, stream);
+}
+
+int gpuar_b200_decode_ex(const uint8_t *d_payload, size_t c, size_t packet_bytes, const uint64_t *d_offsets,
+                         size_t n_packets, uint8_t *d_out, size_t out_cap, void *stream)
+{
+    if (!packet_ok(packet_bytes)) return GPUAR_E_ARG;
+    if (!n_packets) return 0;
+    if (!d_payload || !d_offsets || !d_out) return GPUAR_E_ARG;
+    if (((uintptr_t)d_payload | (uintptr_t)d_out) & 15u) return GPUAR_E_ARG;
+    if (n_packets > 0xFFFFFFF0ull || out_cap < n_packets * packet_bytes) return GPUAR_E_ARG;
+    Scope t(GPUAR_SPAN_DECODE, (cudaStream_t)stream);
+    return ck(launch_decode(d_payload, c + GPUAR_PAD_BYTES, d_offsets, 0, (uint32_t)n_packets, d_out,
+                            (uint32_t)packet_bytes, (cudaStream_t)stream));
 }
 
 int gpuar_b200_decode(const uint8_t *d_payload, size_t c, const uint64_t *d_offsets, size_t n_packets,
                       uint8_t *d_out, size_t out_cap, void *stream)
 {
-    if (!n_packets) return 0;
-    if (!d_payload || !d_offsets || !d_out) return GPUAR_E_ARG;
-    if (((uintptr_t)d_payload | (uintptr_t)d_out) & 15u) return GPUAR_E_ARG;
-    if (n_packets > 0xFFFFFFF0ull || out_cap < n_packets * (size_t)kPacket) return GPUAR_E_ARG;
-    Scope t(GPUAR_SPAN_DECODE, (cudaStream_t)stream);
-    return ck(launch_decode(d_payload, c + GPUAR_PAD_BYTES, d_offsets, 0, (uint32_t)n_packets, d_out,
-                            (cudaStream_t)stream));
+    return gpuar_b200_decode_ex(d_payload, c, kPacket, d_offsets, n_packets, d_out, out_cap, stream);
 }
 
 /* ------------------------------------------------------------------- options */
@@ -479,13 +513,13 @@ void initConstantRange(void) { (void)gpuar_b200_init(); }
 void garCompressExecutor(const uint8_t *source, size_t size, uint8_t *destination, uint32_t numBlocks)
 {
     (void)numBlocks;
-    (void)encode_slots(source, size, destination, kSlot, nullptr, (cudaStream_t)0);
+    (void)encode_slots(source, size, destination, kSlot, nullptr, kPacket, (cudaStream_t)0);
 }
 
 void garDecompressExecutor(const uint8_t *source, size_t size, uint8_t *destination, uint32_t numBlocks)
 {
     (void)numBlocks;
-    (void)launch_decode(source, size, nullptr, kSlot, (uint32_t)(size / kSlot), destination, (cudaStream_t)0);
+    (void)launch_decode(source, size, nullptr, kSlot, (uint32_t)(size / kSlot), destination, kPacket, (cudaStream_t)0);
 }
 
 }  // extern "C"

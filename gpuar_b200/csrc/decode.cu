@@ -55,7 +55,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <bool kRingFeed>
 __global__ void __launch_bounds__(32)
 decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64_t *__restrict__ offsets,
-              uint32_t stride, uint32_t n_packets, uint8_t *__restrict__ out)
+              uint32_t stride, uint32_t n_packets, uint8_t *__restrict__ out, uint32_t packet)
 {
     __shared__ __align__(16) DecShared<kRingFeed> sm;
     const uint32_t lane = lane_id();
@@ -79,7 +79,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     if (mine) {
         const size_t off = offsets ? (size_t)offsets[my] : (size_t)my * stride;
         const uint32_t hdr = (uint32_t)payload[off + 2] | ((uint32_t)payload[off + 3] << 8);   // rawLen, :859
-        raw = min(hdr, kPacket);
+        raw = min(hdr, packet);
         const size_t sp = off + kHdr;                              // first bitstream byte, any alignment
         gp = reinterpret_cast<const uint32_t *>(payload) + (sp >> 2);
         const uint32_t skip = 8u * (uint32_t)(sp & 3u);
@@ -123,7 +123,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     uint32_t L = 0, V = 0;
 
     const uint32_t max_raw = __reduce_max_sync(kFull, raw);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)my * kPacket);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)my * packet);
     uint32_t packed = 0;
 
     // one symbol of this lane's packet; `slot` = position of the byte inside the 32-bit store word
@@ -139,7 +139,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
         refill();
     };
 
-    const uint32_t min_raw = __reduce_min_sync(kFull, mine ? raw : kPacket);
+    const uint32_t min_raw = __reduce_min_sync(kFull, mine ? raw : packet);
     const uint32_t rounds = (max_raw + 31u) >> 5;
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t i0 = r * 32u;
@@ -179,7 +179,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
 }
 
 cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint64_t *d_offsets, uint32_t stride,
-                          uint32_t packets, uint8_t *d_out, cudaStream_t st)
+                          uint32_t packets, uint8_t *d_out, uint32_t packet, cudaStream_t st)
 {
     if (!packets) return cudaSuccess;
     int dev = 0, sms = 148;
@@ -187,9 +187,9 @@ cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint6
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t grid = (packets + 31u) / 32u;
     if (grid <= (uint32_t)sms * 10u)             // at most one resident wave: latency-optimised feed
-        decode_kernel<true><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out);
+        decode_kernel<true><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet);
     else
-        decode_kernel<false><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out);
+        decode_kernel<false><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet);
     count_launch();
     return cudaGetLastError();
 }

@@ -36,7 +36,7 @@ struct EncShared {
 
 __global__ void __launch_bounds__(32)
 encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ slots, uint32_t slot_stride,
-              uint32_t *__restrict__ sizes, uint32_t n_packets)
+              uint32_t *__restrict__ sizes, uint32_t n_packets, uint32_t packet)
 {
     __shared__ __align__(16) EncShared sm;
     const uint32_t lane = lane_id();
@@ -47,11 +47,11 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
     uint64_t root;
     enc_tree_init(root, tree, 32u);                               // all counts 1 (:403-419)
 
-    const size_t off = (size_t)my * kPacket;
-    uint32_t len = 0;                                             // 8192 except for the last packet
-    if (mine) len = (n - off < kPacket) ? (uint32_t)(n - off) : kPacket;
+    const size_t off = (size_t)my * packet;
+    uint32_t len = 0;                                             // `packet` (8192) except for the last packet
+    if (mine) len = (n - off < packet) ? (uint32_t)(n - off) : packet;
     const uint32_t max_len = __reduce_max_sync(kFull, len);
-    const uint32_t min_len = __reduce_min_sync(kFull, mine ? len : kPacket);
+    const uint32_t min_len = __reduce_min_sync(kFull, mine ? len : packet);
 
     uint32_t L = 0, V = 0, pend = 0;
     uint8_t *const slot = slots + (size_t)my * slot_stride;
@@ -311,11 +311,11 @@ shard_concat_kernel(const uint8_t *__restrict__ payload, const uint64_t *__restr
 const void *probe_kernel() { return reinterpret_cast<const void *>(&encode_kernel); }
 
 cudaError_t launch_encode_slots(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t slot_stride,
-                                uint32_t *d_sizes, cudaStream_t st)
+                                uint32_t *d_sizes, uint32_t packet, cudaStream_t st)
 {
-    const uint32_t packets = (uint32_t)((n + kPacket - 1) / kPacket);
+    const uint32_t packets = (uint32_t)((n + packet - 1) / packet);
     if (!packets) return cudaSuccess;
-    encode_kernel<<<(packets + 31u) / 32u, 32, 0, st>>>(d_in, n, d_slots, slot_stride, d_sizes, packets);
+    encode_kernel<<<(packets + 31u) / 32u, 32, 0, st>>>(d_in, n, d_slots, slot_stride, d_sizes, packets, packet);
     count_launch();
     return cudaGetLastError();
 }

@@ -111,18 +111,18 @@ __device__ __forceinline__ void model_warp(WsShared &sm, uint64_t *tree, const u
 
 __global__ void __launch_bounds__(128)
 encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ slots, uint32_t slot_stride,
-                 uint32_t *__restrict__ sizes, uint32_t n_packets)
+                 uint32_t *__restrict__ sizes, uint32_t n_packets, uint32_t packet)
 {
     __shared__ __align__(16) WsShared sm;
     const uint32_t lane = lane_id();
     const uint32_t role = threadIdx.x >> 5;
     const uint32_t my = blockIdx.x * 32u + lane;
     const bool mine = my < n_packets;
-    const size_t off = (size_t)my * kPacket;
+    const size_t off = (size_t)my * packet;
     uint32_t len = 0;
-    if (mine) len = (n - off < kPacket) ? (uint32_t)(n - off) : kPacket;
+    if (mine) len = (n - off < packet) ? (uint32_t)(n - off) : packet;
     const uint32_t max_len = __reduce_max_sync(kFull, len);      // identical in the four warps
-    const uint32_t min_len = __reduce_min_sync(kFull, mine ? len : kPacket);
+    const uint32_t min_len = __reduce_min_sync(kFull, mine ? len : packet);
     const uint32_t rounds = (max_len + kRound - 1u) / kRound;
     uint64_t *const tree = &sm.tree[0][lane];
 
@@ -222,11 +222,11 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
 }
 
 cudaError_t launch_encode_slots_ws(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t slot_stride,
-                                   uint32_t *d_sizes, cudaStream_t st)
+                                   uint32_t *d_sizes, uint32_t packet, cudaStream_t st)
 {
-    const uint32_t packets = (uint32_t)((n + kPacket - 1) / kPacket);
+    const uint32_t packets = (uint32_t)((n + packet - 1) / packet);
     if (!packets) return cudaSuccess;
-    encode_ws_kernel<<<(packets + 31u) / 32u, 128, 0, st>>>(d_in, n, d_slots, slot_stride, d_sizes, packets);
+    encode_ws_kernel<<<(packets + 31u) / 32u, 128, 0, st>>>(d_in, n, d_slots, slot_stride, d_sizes, packets, packet);
     count_launch();
     return cudaGetLastError();
 }

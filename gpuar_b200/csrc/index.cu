@@ -6,7 +6,7 @@
 // A serial walk costs one dependent memory access per packet, so here it is parallel:
 //
 //   1. mark   every byte offset o is tested for "could start a packet":
-//             5 <= compLen <= 8704, o + compLen <= C, and rawLen == 8192 -- or the packet
+//             5 <= compLen <= packet+512, o + compLen <= C, and rawLen == packet (8192) -- or the packet
 //             ends exactly at C (the last packet may be short).  Compressed data looks
 //             random, so false candidates are ~C/500k; true starts always qualify.
 //   2. emit   single-pass decoupled-look-back scan over the candidate bitmap writes the
@@ -76,7 +76,8 @@ __device__ __forceinline__ uint32_t ld16(const uint8_t *p) { return (uint32_t)p[
 
 // ---- 1. mark: thread = 32 consecutive offsets = one bitmap word
 __global__ void __launch_bounds__(kMarkThreads)
-index_mark_kernel(const uint8_t *__restrict__ payload, size_t c, uint32_t *__restrict__ bitmap, size_t words)
+index_mark_kernel(const uint8_t *__restrict__ payload, size_t c, uint32_t *__restrict__ bitmap, size_t words,
+                  uint32_t packet)
 {
     const size_t w = (size_t)blockIdx.x * kMarkThreads + threadIdx.x;
     if (w >= words) return;
@@ -93,8 +94,8 @@ index_mark_kernel(const uint8_t *__restrict__ payload, size_t c, uint32_t *__res
         const uint32_t four = __funnelshift_r(x[q], x[q + 1], s);   // bytes o..o+3
         const uint32_t len = four & 0xFFFFu, raw = four >> 16;
         const size_t o = o0 + j;
-        bool ok = len > kHdr && len <= kSlot && o + len <= c;
-        ok = ok && (raw == kPacket || (o + len == c && raw >= 1u && raw <= kPacket));
+        bool ok = len > kHdr && len <= packet + 512u && o + len <= c;
+        ok = ok && (raw == packet || (o + len == c && raw >= 1u && raw <= packet));
         bits |= (uint32_t)ok << j;
     }
     bitmap[w] = bits;
@@ -213,7 +214,7 @@ index_lift_kernel(const uint32_t *__restrict__ prev, uint32_t *__restrict__ next
 __global__ void index_finish_kernel(const uint8_t *__restrict__ payload, size_t c, const uint64_t *__restrict__ cand,
                                     uint32_t cap, IndexCtl *__restrict__ ctl, const uint32_t *__restrict__ jump,
                                     uint32_t levels, uint64_t *__restrict__ offsets, size_t max_packets,
-                                    uint64_t *__restrict__ result)
+                                    uint64_t *__restrict__ result, uint32_t packet)
 {
     if (threadIdx.x || blockIdx.x) return;
     ctl->serial = 0;
@@ -240,7 +241,7 @@ __global__ void index_finish_kernel(const uint8_t *__restrict__ payload, size_t 
             const uint64_t packets = hops + 1u;
             const uint64_t last_raw = ld16(payload + cand[pos] + 2);
             result[0] = packets;
-            result[1] = (packets - 1u) * kPacket + last_raw;
+            result[1] = (packets - 1u) * packet + last_raw;
             result[2] = packets <= max_packets ? 0ull : (uint64_t)(int64_t)-1;   // GPUAR_E_ARG
             result[3] = n;
             return;
@@ -254,7 +255,7 @@ __global__ void index_finish_kernel(const uint8_t *__restrict__ payload, size_t 
         if (c - o < kHdr) { status = -2; break; }
         const uint64_t len = ld16(payload + o), raw = ld16(payload + o + 2);
         if (len <= kHdr || len > c - o) { status = -2; break; }
-        if (raw == 0 || raw > kPacket || (raw != kPacket && o + len != c)) { status = -4; break; }
+        if (raw == 0 || raw > packet || (raw != packet && o + len != c)) { status = -4; break; }
         if (k < max_packets) offsets[k] = o; else status = -1;
         ++k;
         raw_total += raw;
@@ -287,7 +288,7 @@ index_rank_kernel(const uint64_t *__restrict__ cand, uint32_t cap, const IndexCt
 }
 
 cudaError_t launch_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets, size_t max_packets,
-                         uint64_t *d_result, void *d_scratch, size_t scratch_bytes, cudaStream_t st)
+                         uint64_t *d_result, void *d_scratch, size_t scratch_bytes, uint32_t packet, cudaStream_t st)
 {
     const IndexPlan p = make_plan(c);
     if (scratch_bytes < p.total) return cudaErrorInvalidValue;
@@ -305,7 +306,7 @@ cudaError_t launch_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets
     if (e != cudaSuccess) return e;
     if (c) {
         index_mark_kernel<<<(unsigned)((p.words + kMarkThreads - 1) / kMarkThreads), kMarkThreads, 0, st>>>(
-            d_payload, c, bitmap, p.words);
+            d_payload, c, bitmap, p.words, packet);
         index_emit_kernel<<<(unsigned)p.tiles, kEmitThreads, 0, st>>>(bitmap, p.words, cand, p.cap, desc, ticket,
                                                                       ctl, p.tiles);
         // candidates of a well-formed stream: one per packet plus ~c/500k false ones; the grid
@@ -318,7 +319,7 @@ cudaError_t launch_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets
         count_launch(3 + (int)p.levels - 1);
     }
     index_finish_kernel<<<1, 32, 0, st>>>(d_payload, c, cand, p.cap, ctl, jump, p.levels, d_offsets, max_packets,
-                                          d_result);
+                                          d_result, packet);
     count_launch();
     if (c) {
         // at most one packet per 5 payload bytes; well-formed streams have far fewer

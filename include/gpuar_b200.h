@@ -92,6 +92,22 @@ int gpuar_b200_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets, si
 int gpuar_b200_decode(const uint8_t *d_payload, size_t c, const uint64_t *d_offsets, size_t n_packets,
                       uint8_t *d_out, size_t out_cap, void *stream);
 
+/* ------------------------------------------------ other packet sizes (config sweep)
+ * The packet size is a compile-time constant of the reference (gpu.h:12-13) and is not recorded
+ * in the .gip; a reference rebuilt with another UNCOMPRESSED_PACKET_SIZE produces and reads a
+ * different dialect.  The _ex entry points take it as a run-time argument: any multiple of 16
+ * from 16 to 16112 (the reference's own limit 2^14 - 256, compressor.cpp:13); slots are
+ * packet_bytes + 512.  packet_bytes = 8192 is exactly the plain entry points. */
+size_t gpuar_b200_payload_bound_ex(size_t n, size_t packet_bytes);
+size_t gpuar_b200_encode_scratch_bytes_ex(size_t n, size_t packet_bytes);
+int gpuar_b200_encode_ex(const uint8_t *d_in, size_t n, size_t packet_bytes, uint8_t *d_payload, size_t payload_cap,
+                         uint64_t *d_payload_bytes, uint32_t *d_packet_sizes, void *d_scratch, size_t scratch_bytes,
+                         void *stream);
+int gpuar_b200_index_ex(const uint8_t *d_payload, size_t c, size_t packet_bytes, uint64_t *d_offsets,
+                        size_t max_packets, uint64_t *d_result, void *d_scratch, size_t scratch_bytes, void *stream);
+int gpuar_b200_decode_ex(const uint8_t *d_payload, size_t c, size_t packet_bytes, const uint64_t *d_offsets,
+                         size_t n_packets, uint8_t *d_out, size_t out_cap, void *stream);
+
 /* ------------------------------------------------- host-buffer entry points
  * Whole .gip image in host memory <-> raw bytes in host memory on the current
  * device: staging, H2D, kernels, D2H, header.  Synchronous.  What a caller of

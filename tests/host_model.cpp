@@ -38,13 +38,13 @@ uint32_t host_model_encode_packet(const uint8_t *x, uint32_t n, uint8_t *slot, u
     return finish_packet(out, L, pend, slot, n);
 }
 
-size_t host_model_encode_stream(const uint8_t *in, size_t n, uint8_t *payload)
+size_t host_model_encode_stream(const uint8_t *in, size_t n, uint8_t *payload, uint32_t packet)
 {
-    std::vector<uint8_t> slot(kSlot + 16);
+    std::vector<uint8_t> slot(packet + 512 + 16);
     size_t pos = 0;
-    for (size_t off = 0; off < n; off += kPacket) {
-        const uint32_t m = (uint32_t)(n - off < kPacket ? n - off : kPacket);
-        const uint32_t len = host_model_encode_packet(in + off, m, slot.data(), kSlot);
+    for (size_t off = 0; off < n; off += packet) {
+        const uint32_t m = (uint32_t)(n - off < packet ? n - off : packet);
+        const uint32_t len = host_model_encode_packet(in + off, m, slot.data(), packet + 512);
         memcpy(payload + pos, slot.data(), len);
         pos += len;
     }
@@ -75,7 +75,7 @@ uint32_t host_model_decode_packet(const uint8_t *payload, size_t readable, size_
     uint32_t code = in.take(16u);
     if (in.hungry()) { in.feed(ahead); ++wp; ahead = word(wp); }
     uint32_t L = 0, V = 0;
-    for (uint32_t i = 0; i < raw && i < kPacket; ++i) {
+    for (uint32_t i = 0; i < raw; ++i) {
         const uint32_t T = 256u + i;
         uint32_t sh;
         const uint32_t m = magic_for(T, sh);
@@ -88,15 +88,15 @@ uint32_t host_model_decode_packet(const uint8_t *payload, size_t readable, size_
         code = advance_code(code, k, u, in);
         if (in.hungry()) { in.feed(ahead); ++wp; ahead = word(wp); }
     }
-    return raw < kPacket ? raw : kPacket;
+    return raw;
 }
 
 // exhaustive-ish check of the reciprocal division: for every total T and for numerators
 // around every multiple of T up to max_n (plus random ones): returns the number of mismatches
-uint64_t host_model_check_division(uint32_t max_n)
+uint64_t host_model_check_division(uint32_t max_n, uint32_t packet)
 {
     uint64_t bad = 0;
-    for (uint32_t T = 256; T < 256 + kPacket; ++T) {
+    for (uint32_t T = 256; T < 256 + packet; ++T) {
         uint32_t sh;
         const uint32_t m = magic_for(T, sh);
         for (uint64_t q = 0; q * T <= max_n; q += 1 + q / 64) {
@@ -112,10 +112,10 @@ uint64_t host_model_check_division(uint32_t max_n)
 }
 
 // the float-estimated divide of the decoder against integer division, on a lattice of states
-uint64_t host_model_check_unscale(uint32_t stride)
+uint64_t host_model_check_unscale(uint32_t stride, uint32_t packet)
 {
     uint64_t bad = 0;
-    for (uint32_t T = 256; T < 256 + kPacket; T += 37)
+    for (uint32_t T = 256; T < 256 + packet; T += 37)
         for (uint32_t range = 16385; range <= 65536; range += stride)
             for (uint32_t cl = 0; cl < range; cl += 1 + range / 97) {
                 const uint32_t L = 0, V = 65536u - range, code = cl;

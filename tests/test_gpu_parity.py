@@ -95,6 +95,27 @@ def test_both_encode_kernels_are_bit_exact(dev, path):
         _lib.set_option(_lib.OPT_ENCODE_PATH, _lib.ENCODE_AUTO)
 
 
+@pytest.mark.parametrize("path", ["fused", "ws"])
+@pytest.mark.parametrize("packet", [4096, 8192, 12288, 16112])
+def test_packet_size_sweep_equals_rebuilt_reference(dev, packet, path):
+    """BASELINE config 5: other packet sizes.  Goldens come from the reference rebuilt with gpu.h:12
+    patched (tests/golden/sweep.json).  The device index/decoder must read them back."""
+    from _vectors import SWEEP
+    from gpuar_b200 import _lib
+    rec = SWEEP[str(packet)]
+    data = D.mixed(rec["seed"], rec["n"])
+    _lib.set_option(_lib.OPT_ENCODE_PATH, _lib.ENCODE_FUSED if path == "fused" else _lib.ENCODE_WS)
+    try:
+        pay = dev.encode_bytes(to_dev(data), packet=packet)
+    finally:
+        _lib.set_option(_lib.OPT_ENCODE_PATH, _lib.ENCODE_AUTO)
+    got = pay.cpu().numpy()
+    assert got.size == rec["payload_bytes"] and md5(got) == rec["payload_md5"]
+    assert np.array_equal(got, O.encode(data, packet))
+    back = dev.decode_bytes(pay, packet=packet).cpu().numpy()
+    assert np.array_equal(back, data)
+
+
 # ------------------------------------------------------------------ index
 @pytest.mark.parametrize("name", SMALL)
 def test_index_equals_chain_walk(dev, name):

@@ -25,20 +25,20 @@ def model():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", src, "-o", SO])
     lib = C.CDLL(SO)
     lib.host_model_encode_stream.restype = C.c_size_t
-    lib.host_model_encode_stream.argtypes = [O._u8p, C.c_size_t, O._u8p]
+    lib.host_model_encode_stream.argtypes = [O._u8p, C.c_size_t, O._u8p, C.c_uint32]
     lib.host_model_decode_packet.restype = C.c_uint32
     lib.host_model_decode_packet.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p]
     lib.host_model_check_division.restype = C.c_uint64
-    lib.host_model_check_division.argtypes = [C.c_uint32]
+    lib.host_model_check_division.argtypes = [C.c_uint32, C.c_uint32]
     lib.host_model_check_unscale.restype = C.c_uint64
-    lib.host_model_check_unscale.argtypes = [C.c_uint32]
+    lib.host_model_check_unscale.argtypes = [C.c_uint32, C.c_uint32]
     return lib
 
 
-def model_encode(lib, data):
-    buf = np.zeros(O.n_packets(data.size) * O.SLOT + 64, np.uint8)
+def model_encode(lib, data, packet=8192):
+    buf = np.zeros(O.n_packets(data.size, packet) * (packet + 512) + 64, np.uint8)
     src = data if data.size else np.zeros(1, np.uint8)
-    return buf[: lib.host_model_encode_stream(O._ptr(src), data.size, O._ptr(buf))].copy()
+    return buf[: lib.host_model_encode_stream(O._ptr(src), data.size, O._ptr(buf), packet)].copy()
 
 
 def model_decode(lib, pay, n):
@@ -53,12 +53,15 @@ def model_decode(lib, pay, n):
 
 
 def test_reciprocal_division_is_exact(model):
-    # floor(n / T) for every total T = 256..8447 around every multiple of T up to the largest numerator
-    assert model.host_model_check_division(8448 * 65536) == 0
+    # floor(n / T) for every total T = 256..8447 around every multiple of T up to the largest numerator,
+    # and for the largest packet size the format admits (16112: totals up to 16367, numerators < 2^30)
+    assert model.host_model_check_division(8448 * 65536, 8192) == 0
+    assert model.host_model_check_division(16368 * 65536, 16112) == 0
 
 
 def test_float_estimated_divide_is_exact(model):
-    assert model.host_model_check_unscale(13) == 0
+    assert model.host_model_check_unscale(13, 8192) == 0
+    assert model.host_model_check_unscale(29, 16112) == 0
 
 
 @pytest.mark.parametrize("name", SMALL)
@@ -76,6 +79,16 @@ def test_kernel_math_ragged_lengths(model, n):
         pay = model_encode(model, data)
         assert np.array_equal(pay, O.encode(data))
         assert np.array_equal(model_decode(model, pay, n), data)
+
+
+@pytest.mark.parametrize("packet", [4096, 12288, 16112])
+def test_kernel_math_other_packet_sizes(model, packet):
+    from _vectors import SWEEP
+    rec = SWEEP[str(packet)]
+    data = D.mixed(rec["seed"], rec["n"])
+    pay = model_encode(model, data, packet)
+    assert pay.size == rec["payload_bytes"] and md5(pay) == rec["payload_md5"]
+    assert np.array_equal(model_decode(model, pay, data.size), data)
 
 
 def test_kernel_math_long_underflow_runs(model):
