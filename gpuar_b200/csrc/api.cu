@@ -334,10 +334,13 @@ int gpuar_b200_compress_host(const uint8_t *in, size_t n, uint8_t *gip, size_t g
     int rc = host_path(&h);
     if (rc) return rc;
 
-    // chunks of 2048 packets (16 MiB) rotate over kLanes streams: H2D, encode and
-    // scan+compact of chunk k overlap the D2H of chunk k-1; the host only waits for the
-    // 8-byte total of a chunk to know where the next one lands in the image
-    const size_t chunk = (size_t)2048 * kPacket;
+    // chunks rotate over kLanes streams: H2D, encode and scan+compact of chunk k overlap the D2H
+    // of chunk k-1; the host only waits for the 8-byte total of a chunk to know where the next
+    // one lands in the image.  A chunk's kernels take about the same time from 1 to ~20 000
+    // packets (a packet is a serial chain), so small inputs use 16 MiB chunks to start the
+    // pipeline early and large ones 64 MiB chunks to keep enough packets in flight.
+    size_t chunk = align_up(n / 8 + 1, kPacket);
+    chunk = chunk < ((size_t)16 << 20) ? ((size_t)16 << 20) : chunk > ((size_t)64 << 20) ? ((size_t)64 << 20) : chunk;
     const size_t chunks = (n + chunk - 1) / chunk;
     size_t pos = GPUAR_FILE_HEADER;
     cudaError_t e = cudaSuccess;
