@@ -70,6 +70,8 @@ GPUAR_HD uint32_t div_total(uint32_t n, uint32_t m, uint32_t sh) { return mulhi3
 //   in : L, V; lo = cum[s], hi = cum[s+1]; (m, sh) for the current total
 //   out: L, V renormalised; k = equal MSBs shifted out (0..16); u = underflow shifts (0..15);
 //        U1 = upper bound before renormalisation (its top k bits are the output bits)
+// Reference loop in closed form: always k matching-MSB shifts, then u underflow shifts, and
+// L = (L1 << (k+u)) & 0x7FFF, V = (V1 << (k+u)) & 0x7FFF.
 GPUAR_HD void narrow_renorm(uint32_t &L, uint32_t &V, uint32_t lo, uint32_t hi, uint32_t m, uint32_t sh,
                             uint32_t &k, uint32_t &u, uint32_t &U1)
 {

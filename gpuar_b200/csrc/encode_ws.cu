@@ -190,19 +190,26 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
             const bool full = i0 + kRound <= min_len;
             bar_sync(kFFull + b);
             if (full) {
-#pragma unroll 4
-                for (uint32_t j = 0; j < kRound; ++j) {
-                    const uint32_t f = sm.ring_f[b][j][lane];
-                    uint32_t k = f & 31u, u = (f >> 5) & 15u;
-                    const uint32_t U1 = (f >> 9) & 0xFFFFu;
-                    if (__any_sync(kFull, emit_is_long(pend, k))) {           // warp-uniform, almost never
-                        if (emit_is_long(pend, k)) {
-                            emit_long(out, pend, k, u, U1);
-                            k = 0;
-                            u = 0;
-                        }
+                // four steps per block.  The rare long-underflow path needs pend > 16 at a step
+                // with k != 0; pend grows by at most the u's of the group, so one warp-uniform
+                // vote on (pend + sum of u) covers the whole group and the common block has no
+                // branch at all: its four ring loads issue together.
+#pragma unroll 1
+                for (uint32_t j0 = 0; j0 < kRound; j0 += 4u) {
+                    uint32_t f[4];
+#pragma unroll
+                    for (uint32_t j = 0; j < 4u; ++j) f[j] = sm.ring_f[b][j0 + j][lane];
+                    const uint32_t usum = ((f[0] >> 5) & 15u) + ((f[1] >> 5) & 15u) + ((f[2] >> 5) & 15u) +
+                                          ((f[3] >> 5) & 15u);
+                    if (__any_sync(kFull, pend + usum > 16u)) {
+#pragma unroll
+                        for (uint32_t j = 0; j < 4u; ++j)
+                            emit_symbol(out, pend, f[j] & 31u, (f[j] >> 5) & 15u, (f[j] >> 9) & 0xFFFFu);
+                    } else {
+#pragma unroll
+                        for (uint32_t j = 0; j < 4u; ++j)
+                            emit_field(out, pend, f[j] & 31u, (f[j] >> 5) & 15u, (f[j] >> 9) & 0xFFFFu);
                     }
-                    emit_field(out, pend, k, u, U1);
                 }
             } else {
 #pragma unroll 1

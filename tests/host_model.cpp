@@ -111,6 +111,43 @@ uint64_t host_model_check_division(uint32_t max_n, uint32_t packet)
     return bad;
 }
 
+// narrow_renorm against the reference's bit-at-a-time loop (gpuar_kernel.cu:256-288, 321-367) on
+// random reachable states: returns the number of mismatches in (L, U, k, u)
+uint64_t host_model_check_renorm(uint64_t seed, uint32_t count, uint32_t packet)
+{
+    uint64_t bad = 0, x = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    for (uint32_t n = 0; n < count; ++n) {
+        // a renormalised state: MSBs differ and not the 01../10.. pattern
+        uint32_t lo16, hi16;
+        do {
+            lo16 = (uint32_t)rnd() & 0x7FFFu;
+            hi16 = ((uint32_t)rnd() & 0x7FFFu) | 0x8000u;
+        } while ((lo16 & 0x4000u) && !(hi16 & 0x4000u));
+        const uint32_t T = 256u + (uint32_t)(rnd() % packet);
+        uint32_t cl = (uint32_t)(rnd() % T), ch = cl + 1u + (uint32_t)(rnd() % (T - cl));
+        if (n & 1u) ch = cl + 1u;                                  // narrow symbols stress the shifts
+        if (ch > T) ch = T;
+        // reference arithmetic
+        uint32_t range = hi16 - lo16 + 1u;
+        uint16_t U = (uint16_t)(lo16 + (uint16_t)(ch * range / T) - 1u), Lr = (uint16_t)(lo16 + (uint16_t)(cl * range / T));
+        const uint16_t U1ref = U;
+        uint32_t kk = 0, uu = 0;
+        for (;;) {
+            if (((U ^ Lr) & 0x8000u) == 0) { ++kk; }
+            else if ((Lr & 0x4000u) && !(U & 0x4000u)) { ++uu; Lr &= 0x3FFFu; U |= 0x4000u; }
+            else break;
+            Lr = (uint16_t)(Lr << 1);
+            U = (uint16_t)((U << 1) | 1u);
+        }
+        uint32_t L = lo16, V = (~hi16) & 0xFFFFu, sh, k, u, U1;
+        const uint32_t m = magic_for(T, sh);
+        narrow_renorm(L, V, cl, ch, m, sh, k, u, U1);
+        bad += (L != Lr) || ((V ^ 0xFFFFu) != U) || (k != kk) || (u != uu) || (U1 != U1ref);
+    }
+    return bad;
+}
+
 // the float-estimated divide of the decoder against integer division, on a lattice of states
 uint64_t host_model_check_unscale(uint32_t stride, uint32_t packet)
 {

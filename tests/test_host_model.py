@@ -30,6 +30,8 @@ def model():
     lib.host_model_decode_packet.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p]
     lib.host_model_check_division.restype = C.c_uint64
     lib.host_model_check_division.argtypes = [C.c_uint32, C.c_uint32]
+    lib.host_model_check_renorm.restype = C.c_uint64
+    lib.host_model_check_renorm.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
     lib.host_model_check_unscale.restype = C.c_uint64
     lib.host_model_check_unscale.argtypes = [C.c_uint32, C.c_uint32]
     return lib
@@ -57,6 +59,12 @@ def test_reciprocal_division_is_exact(model):
     # and for the largest packet size the format admits (16112: totals up to 16367, numerators < 2^30)
     assert model.host_model_check_division(8448 * 65536, 8192) == 0
     assert model.host_model_check_division(16368 * 65536, 16112) == 0
+
+
+def test_closed_form_renormalisation_equals_reference_loop(model):
+    # 4M random reachable coder states per packet size against the bit-at-a-time loop
+    assert model.host_model_check_renorm(1, 4_000_000, 8192) == 0
+    assert model.host_model_check_renorm(2, 2_000_000, 16112) == 0
 
 
 def test_float_estimated_divide_is_exact(model):
