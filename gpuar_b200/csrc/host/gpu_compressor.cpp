@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <future>
 
 #include "../../../include/gpuar_b200.h"
 
@@ -24,8 +25,10 @@ GpuCompressor::GpuCompressor(std::size_t segmentBytes) : segmentBytes_(std::max<
 
 GpuCompressor::~GpuCompressor()
 {
-    if (in_) gpuar_b200_host_free(in_);
-    if (out_) gpuar_b200_host_free(out_);
+    for (int b = 0; b < 2; ++b) {
+        if (in_[b]) gpuar_b200_host_free(in_[b]);
+        if (out_[b]) gpuar_b200_host_free(out_[b]);
+    }
 }
 
 void GpuCompressor::chooseDevice(int id)
@@ -37,15 +40,19 @@ void GpuCompressor::chooseDevice(int id)
 void GpuCompressor::reserve(std::size_t inBytes, std::size_t outBytes)
 {
     if (inBytes > inCap_) {
-        if (in_) gpuar_b200_host_free(in_);
-        in_ = nullptr;
-        check(gpuar_b200_host_alloc(inBytes, (void **)&in_), "gpuar_b200_host_alloc");
+        for (int b = 0; b < 2; ++b) {
+            if (in_[b]) gpuar_b200_host_free(in_[b]);
+            in_[b] = nullptr;
+            check(gpuar_b200_host_alloc(inBytes, (void **)&in_[b]), "gpuar_b200_host_alloc");
+        }
         inCap_ = inBytes;
     }
     if (outBytes > outCap_) {
-        if (out_) gpuar_b200_host_free(out_);
-        out_ = nullptr;
-        check(gpuar_b200_host_alloc(outBytes, (void **)&out_), "gpuar_b200_host_alloc");
+        for (int b = 0; b < 2; ++b) {
+            if (out_[b]) gpuar_b200_host_free(out_[b]);
+            out_[b] = nullptr;
+            check(gpuar_b200_host_alloc(outBytes, (void **)&out_[b]), "gpuar_b200_host_alloc");
+        }
         outCap_ = outBytes;
     }
 }
@@ -66,25 +73,40 @@ CompressionInfo GpuCompressor::compress(ProgressMonitor *monitor)
 
     const std::size_t seg = std::min<std::size_t>(segmentBytes_, std::max<std::size_t>(info.uncompressedFileSize, 1));
     reserve(seg + 16, kFileHeader + gpuar_b200_payload_bound(seg));
-    for (;;) {
-        io.start();
-        const std::size_t got = std::fread(in_, 1, seg, in.get());
-        io.stop();
-        if (!got) break;
+    // three-stage pipeline over segments: read(i+1) | device(i) | write(i-1)
+    auto readSegment = [&](int b) { return std::fread(in_[b], 1, seg, in.get()); };
+    auto writeSegment = [&](int b, std::size_t payload) {
+        // the per-segment header is dropped: packets are self-delimiting
+        return payload == 0 || std::fwrite(out_[b] + kFileHeader, payload, 1, out.get()) == 1;
+    };
+    io.start();
+    std::size_t got = readSegment(0);
+    io.stop();
+    std::future<bool> writing;
+    for (int i = 0; got; ++i) {
+        const int b = i & 1;
+        std::future<std::size_t> reading;
+        if (got == seg) reading = std::async(std::launch::async, readSegment, b ^ 1);
         proc.start();
         std::size_t image = 0;
-        check(gpuar_b200_compress_host(in_, got, out_, outCap_, &image), "gpuar_b200_compress_host");
+        // write(i-1) may still be running on out_[b^1]; out_[b] is free (write(i-2) finished before write(i-1) started)
+        check(gpuar_b200_compress_host(in_[b], got, out_[b], outCap_, &image), "gpuar_b200_compress_host");
         proc.stop();
         io.start();
-        const std::size_t payload = image - kFileHeader;       // the per-segment header is dropped:
-        if (payload && std::fwrite(out_ + kFileHeader, payload, 1, out.get()) != 1)   // packets are self-delimiting
-            throw std::runtime_error("Write compressed data to output file failed");
+        if (writing.valid() && !writing.get()) throw std::runtime_error("Write compressed data to output file failed");
+        const std::size_t payload = image - kFileHeader;
+        writing = std::async(std::launch::async, writeSegment, b, payload);
         io.stop();
         info.processedUncompressedSize += got;
         info.compressedFileSize += payload;
         monitor->updateProgress(&info);
-        if (got < seg) break;
+        io.start();
+        got = reading.valid() ? reading.get() : 0;
+        io.stop();
     }
+    io.start();
+    if (writing.valid() && !writing.get()) throw std::runtime_error("Write compressed data to output file failed");
+    io.stop();
 
     io.start();                                                  // header last, as gpu_compressor.cpp:199-208
     gpuar_b200_write_header(header, info.uncompressedFileSize, info.compressedFileSize);
@@ -123,7 +145,9 @@ CompressionInfo GpuCompressor::decompress(ProgressMonitor *monitor)
     std::size_t begin = 0, end = 0;
     std::uint64_t remaining = fileBytes - kFileHeader;
     std::uint64_t produced = 0;
-    std::uint8_t *const pay = in_ + kFileHeader;
+    std::uint8_t *const pay = in_[0] + kFileHeader;
+    std::future<bool> writing;
+    int ob = 0;
     while (remaining || end > begin) {
         if (begin && (end - begin < kSlotBytes || begin > segPayload / 2)) {      // make room at the tail
             std::memmove(pay, pay + begin, end - begin);
@@ -151,13 +175,18 @@ CompressionInfo GpuCompressor::decompress(ProgressMonitor *monitor)
         std::uint8_t *image = pay + begin - kFileHeader;         // a .gip image of just this segment
         gpuar_b200_write_header(image, raw, kFileHeader + (cut - begin));
         std::size_t got = 0;
-        check(gpuar_b200_decompress_host(image, kFileHeader + (cut - begin), out_, outCap_, &got),
+        check(gpuar_b200_decompress_host(image, kFileHeader + (cut - begin), out_[ob], outCap_, &got),
               "gpuar_b200_decompress_host");
         proc.stop();
         if (got != raw) throw std::runtime_error("Incorrect file format");
-        io.start();
-        if (got && std::fwrite(out_, got, 1, out.get()) != 1)
-            throw std::runtime_error("Write uncompressed data to output file failed");
+        io.start();                                              // write(i) overlaps read + device work of i+1
+        if (writing.valid() && !writing.get()) throw std::runtime_error("Write uncompressed data to output file failed");
+        {
+            std::uint8_t *src = out_[ob];
+            std::FILE *f = out.get();
+            writing = std::async(std::launch::async, [src, got, f] { return got == 0 || std::fwrite(src, got, 1, f) == 1; });
+        }
+        ob ^= 1;
         io.stop();
         begin = cut;
         produced += got;
@@ -165,6 +194,9 @@ CompressionInfo GpuCompressor::decompress(ProgressMonitor *monitor)
         if (produced > info.uncompressedFileSize) info.uncompressedFileSize = produced;
         monitor->updateProgress(&info);
     }
+    io.start();
+    if (writing.valid() && !writing.get()) throw std::runtime_error("Write uncompressed data to output file failed");
+    io.stop();
     info.uncompressedFileSize = produced;
     info.processTime = proc.ms();
     info.ioTime = io.ms();

@@ -6,8 +6,10 @@
 namespace gip {
 
 class GpuCompressor : public Compressor {
-    std::uint8_t *in_ = nullptr;       // page-locked staging: one segment of input
-    std::uint8_t *out_ = nullptr;      // page-locked staging: one segment of output
+    // page-locked staging, double buffered: while the device works on segment i, segment i+1 is
+    // read from the input file and segment i-1 is written to the output file by helper threads
+    std::uint8_t *in_[2] = {nullptr, nullptr};
+    std::uint8_t *out_[2] = {nullptr, nullptr};
     std::size_t inCap_ = 0, outCap_ = 0;
     std::size_t segmentBytes_;         // raw bytes handled per library call (multiple of 8192)
 
