@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgpuar_b200.so")
+# GPUAR_B200_LIB points at an alternative build of the same library (A/B measurements)
+LIB_PATH = os.environ.get("GPUAR_B200_LIB") or os.path.join(HERE, "libgpuar_b200.so")
 
 PACKET = 8192          # GPUAR_PACKET_BYTES  (reference gpu.h:13)
 SLOT = 8704            # GPUAR_SLOT_BYTES    (reference gpu.h:12)

@@ -182,10 +182,8 @@ GPUAR_HD uint32_t finish_packet(BitSink &out, uint32_t L, uint32_t pend, uint8_t
 // ---- decoder: target = ((code - L + 1) * T - 1) / range  (getUnscaledCode, :703-716)
 // num < 2^30 and 2^14 < range <= 2^16: a float estimate (approximate reciprocal, a few ulp)
 // is within 1 of the quotient; one correction step makes it exact.
-GPUAR_HD uint32_t unscale(uint32_t code, uint32_t L, uint32_t V, uint32_t T)
+GPUAR_HD uint32_t divide_exact(uint32_t num, uint32_t range)      // num < 2^30, 2^14 < range <= 2^16
 {
-    const uint32_t range = 65536u - V - L;
-    const uint32_t num = (((code - L) & 0xFFFFu) + 1u) * T - 1u;
 #if defined(__CUDA_ARCH__)
     float rcp;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(__uint2float_rz(range)));
@@ -197,6 +195,13 @@ GPUAR_HD uint32_t unscale(uint32_t code, uint32_t L, uint32_t V, uint32_t T)
     if (r < 0) --q;
     else if (r >= (int32_t)range) ++q;
     return q;
+}
+
+GPUAR_HD uint32_t unscale(uint32_t code, uint32_t L, uint32_t V, uint32_t T)
+{
+    const uint32_t range = 65536u - V - L;
+    const uint32_t num = (((code - L) & 0xFFFFu) + 1u) * T - 1u;
+    return divide_exact(num, range);
 }
 
 // byte permute of the 8 bytes {b:a} (prmt.b32, default mode).  Selector nibbles 0..7 pick a
@@ -275,6 +280,56 @@ GPUAR_HD uint32_t tree_decode(uint64_t &root, uint64_t *nodes, uint32_t stride, 
         idx = idx * 4u + tree_level(v, rem, room);
         *n = v;
     }
+    {
+        uint64_t *n = nodes + (20u + idx) * stride;
+        uint64_t v = *n;
+        idx = idx * 4u + tree_level(v, rem, room);
+        *n = v;
+    }
+    lo = target - rem;
+    cnt = rem + room;
+    return idx;
+}
+
+// Latency-oriented variant of tree_decode.  target = floor(num / range), so for an integer
+// threshold t:  t <= target  <=>  t * range <= num.  The two top levels are therefore decided
+// with multiplications only, while the divide is still in flight, and the level-1 and
+// level-2 node loads are issued before `target` exists; the two lower levels then run on
+// `target` as in tree_decode.  Same result, the dependent chain is ~2 shared-memory round
+// trips shorter.  (t * range <= 8448 * 65536 < 2^30, num < 2^30: 32-bit compares are exact.)
+GPUAR_HD uint32_t tree_decode_early(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t code, uint32_t L,
+                                    uint32_t V, uint32_t T, uint32_t &lo, uint32_t &cnt)
+{
+    const uint32_t range = 65536u - V - L;
+    const uint32_t num = (((code - L) & 0xFFFFu) + 1u) * T - 1u;
+    // level 0
+    const uint32_t r0 = (uint32_t)root, r1 = (uint32_t)(root >> 32);
+    const uint32_t c0 = (uint32_t)((r0 >> 16) * range <= num) + (uint32_t)((r1 & 0xFFFFu) * range <= num) +
+                        (uint32_t)((r1 >> 16) * range <= num);
+    uint64_t *const p1 = nodes + c0 * stride;
+    uint64_t n1 = *p1;
+    const uint32_t w0 = prmt(r0, r1, 0x3210u + 0x2222u * c0);        // slot c0 | slot c0+1 << 16
+    const uint32_t below0 = w0 & 0xFFFFu;
+    const uint32_t above0 = c0 == 3u ? T : (w0 >> 16);
+    root += 0x0001000100010000ull << (16u * c0);
+    // level 1, absolute thresholds
+    const uint32_t q0 = (uint32_t)n1, q1 = (uint32_t)(n1 >> 32);
+    const uint32_t c1 = (uint32_t)((below0 + (q0 >> 16)) * range <= num) +
+                        (uint32_t)((below0 + (q1 & 0xFFFFu)) * range <= num) +
+                        (uint32_t)((below0 + (q1 >> 16)) * range <= num);
+    uint32_t idx = c0 * 4u + c1;
+    uint64_t *const p2 = nodes + (4u + idx) * stride;
+    uint64_t n2 = *p2;
+    const uint32_t w1 = prmt(q0, q1, 0x3210u + 0x2222u * c1);
+    const uint32_t below1 = below0 + (w1 & 0xFFFFu);
+    const uint32_t above1 = c1 == 3u ? above0 : below0 + (w1 >> 16);
+    n1 += 0x0001000100010000ull << (16u * c1);
+    *p1 = n1;
+    // levels 2 and 3 on the quotient
+    const uint32_t target = divide_exact(num, range);
+    uint32_t rem = target - below1, room = above1 - target;
+    idx = idx * 4u + tree_level(n2, rem, room);
+    *p2 = n2;
     {
         uint64_t *n = nodes + (20u + idx) * stride;
         uint64_t v = *n;

@@ -129,9 +129,9 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     // one symbol of this lane's packet; `slot` = position of the byte inside the 32-bit store word
     auto step = [&](uint32_t i, uint32_t m, uint32_t sh, uint32_t slot) {
         const uint32_t T = 256u + i;
-        const uint32_t target = unscale(code, L, V, T);
         uint32_t lo, cnt;
-        const uint32_t s = tree_decode(root, tree, 32u, target, T, lo, cnt);
+        const uint32_t s = kRingFeed ? tree_decode_early(root, tree, 32u, code, L, V, T, lo, cnt)
+                                     : tree_decode(root, tree, 32u, unscale(code, L, V, T), T, lo, cnt);
         packed |= s << (8u * slot);
         uint32_t k, u, U1;
         narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);

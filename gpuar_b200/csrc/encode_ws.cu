@@ -202,8 +202,8 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
                     const uint32_t usum = ((f[0] >> 5) & 15u) + ((f[1] >> 5) & 15u) + ((f[2] >> 5) & 15u) +
                                           ((f[3] >> 5) & 15u);
                     if (__any_sync(kFull, pend + usum > 16u)) {
-#pragma unroll
-                        for (uint32_t j = 0; j < 4u; ++j)
+#pragma unroll 1
+                        for (uint32_t j = 0; j < 4u; ++j)         // rare path: small code; f[] spills to 16 B of stack here only
                             emit_symbol(out, pend, f[j] & 31u, (f[j] >> 5) & 15u, (f[j] >> 9) & 0xFFFFu);
                     } else {
 #pragma unroll

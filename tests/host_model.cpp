@@ -53,7 +53,7 @@ size_t host_model_encode_stream(const uint8_t *in, size_t n, uint8_t *payload, u
 
 // decode the packet at byte offset `off` of a padded, 4-byte aligned payload exactly as a
 // lane of decode_kernel does; returns bytes produced
-uint32_t host_model_decode_packet(const uint8_t *payload, size_t readable, size_t off, uint8_t *out)
+static uint32_t decode_packet(const uint8_t *payload, size_t readable, size_t off, uint8_t *out, bool early)
 {
     std::vector<uint64_t> tree(kTreeStored);
     uint64_t root;
@@ -79,9 +79,9 @@ uint32_t host_model_decode_packet(const uint8_t *payload, size_t readable, size_
         const uint32_t T = 256u + i;
         uint32_t sh;
         const uint32_t m = magic_for(T, sh);
-        const uint32_t target = unscale(code, L, V, T);
         uint32_t lo, cnt;
-        const uint32_t s = tree_decode(root, tree.data(), 1, target, T, lo, cnt);
+        const uint32_t s = early ? tree_decode_early(root, tree.data(), 1, code, L, V, T, lo, cnt)
+                                 : tree_decode(root, tree.data(), 1, unscale(code, L, V, T), T, lo, cnt);
         out[i] = (uint8_t)s;
         uint32_t k, u, U1;
         narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
@@ -89,6 +89,17 @@ uint32_t host_model_decode_packet(const uint8_t *payload, size_t readable, size_
         if (in.hungry()) { in.feed(ahead); ++wp; ahead = word(wp); }
     }
     return raw;
+}
+
+uint32_t host_model_decode_packet(const uint8_t *payload, size_t readable, size_t off, uint8_t *out)
+{
+    return decode_packet(payload, readable, off, out, false);
+}
+
+// the latency variant (multiplicative top levels) used by decode_kernel<true>
+uint32_t host_model_decode_packet_early(const uint8_t *payload, size_t readable, size_t off, uint8_t *out)
+{
+    return decode_packet(payload, readable, off, out, true);
 }
 
 // exhaustive-ish check of the reciprocal division: for every total T and for numerators

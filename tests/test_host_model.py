@@ -28,6 +28,8 @@ def model():
     lib.host_model_encode_stream.argtypes = [O._u8p, C.c_size_t, O._u8p, C.c_uint32]
     lib.host_model_decode_packet.restype = C.c_uint32
     lib.host_model_decode_packet.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p]
+    lib.host_model_decode_packet_early.restype = C.c_uint32
+    lib.host_model_decode_packet_early.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p]
     lib.host_model_check_division.restype = C.c_uint64
     lib.host_model_check_division.argtypes = [C.c_uint32, C.c_uint32]
     lib.host_model_check_renorm.restype = C.c_uint64
@@ -43,14 +45,15 @@ def model_encode(lib, data, packet=8192):
     return buf[: lib.host_model_encode_stream(O._ptr(src), data.size, O._ptr(buf), packet)].copy()
 
 
-def model_decode(lib, pay, n):
+def model_decode(lib, pay, n, early=False):
+    fn = lib.host_model_decode_packet_early if early else lib.host_model_decode_packet
     c = pay.size
     padded = np.zeros((c + 64 + 15) // 16 * 16, np.uint8)
     padded[:c] = pay
     out = np.zeros(n + O.PACKET, np.uint8)
     pos = 0
     for o in O.index(pay):
-        pos += lib.host_model_decode_packet(O._ptr(padded), c + 64, int(o), out[pos:].ctypes.data_as(O._u8p))
+        pos += fn(O._ptr(padded), c + 64, int(o), out[pos:].ctypes.data_as(O._u8p))
     return out[:pos]
 
 
@@ -79,6 +82,7 @@ def test_kernel_math_matches_reference_golden(model, name):
     pay = model_encode(model, data)
     assert pay.size == rec["payload_bytes"] and md5(pay) == rec["payload_md5"]
     assert np.array_equal(model_decode(model, pay, data.size), data)
+    assert np.array_equal(model_decode(model, pay, data.size, early=True), data)
 
 
 @pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 63, 64, 65, 4095, 8191, 8192])
@@ -87,6 +91,7 @@ def test_kernel_math_ragged_lengths(model, n):
         pay = model_encode(model, data)
         assert np.array_equal(pay, O.encode(data))
         assert np.array_equal(model_decode(model, pay, n), data)
+        assert np.array_equal(model_decode(model, pay, n, early=True), data)
 
 
 @pytest.mark.parametrize("packet", [4096, 12288, 16112])
@@ -97,6 +102,7 @@ def test_kernel_math_other_packet_sizes(model, packet):
     pay = model_encode(model, data, packet)
     assert pay.size == rec["payload_bytes"] and md5(pay) == rec["payload_md5"]
     assert np.array_equal(model_decode(model, pay, data.size), data)
+    assert np.array_equal(model_decode(model, pay, data.size, early=True), data)
 
 
 def test_kernel_math_long_underflow_runs(model):
