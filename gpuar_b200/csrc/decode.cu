@@ -19,7 +19,16 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#ifndef GPUAR_DEC_UNROLL
+#define GPUAR_DEC_UNROLL 4          // steps per unrolled block of the full-round loop (tuning knob)
+#endif
+#ifndef GPUAR_DEC_EARLY_BIG
+#define GPUAR_DEC_EARLY_BIG 0       // 1: multiplicative top levels also in the throughput variant
+#endif
+
 namespace gpuar {
+
+constexpr int kDecUnroll = GPUAR_DEC_UNROLL;
 
 __device__ __forceinline__ const uint32_t *clamp_ptr(const uint32_t *p, const uint32_t *last)
 {
@@ -130,7 +139,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     auto step = [&](uint32_t i, uint32_t m, uint32_t sh, uint32_t slot) {
         const uint32_t T = 256u + i;
         uint32_t lo, cnt;
-        const uint32_t s = kRingFeed ? tree_decode_early(root, tree, 32u, code, L, V, T, lo, cnt)
+        const uint32_t s = (kRingFeed || GPUAR_DEC_EARLY_BIG) ? tree_decode_early(root, tree, 32u, code, L, V, T, lo, cnt)
                                      : tree_decode(root, tree, 32u, unscale(code, L, V, T), T, lo, cnt);
         packed |= s << (8u * slot);
         uint32_t k, u, U1;
@@ -148,7 +157,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
         sh = shift_for(256u + i0);                                 // the shift is uniform over the round
         if (i0 + 32u <= min_raw) {
             // every lane of the warp has all 32 positions: no per-lane predicates
-#pragma unroll 4
+#pragma unroll kDecUnroll
             for (uint32_t j = 0; j < 32u; ++j) {
                 step(i0 + j, __shfl_sync(kFull, m_l, j), sh, j & 3u);
                 if ((j & 3u) == 3u) {

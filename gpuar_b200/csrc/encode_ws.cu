@@ -15,9 +15,14 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#ifndef GPUAR_WS_CODER_UNROLL
+#define GPUAR_WS_CODER_UNROLL 8     // tuning knob: steps per unrolled block of the CODER warp
+#endif
+
 namespace gpuar {
 
 constexpr uint32_t kRound = 32;
+constexpr int kCoderUnroll = GPUAR_WS_CODER_UNROLL;
 
 struct WsShared {
     uint64_t tree[kTreeStored][32];      // 21504 B: nodes 0-3 MODEL-A, nodes 4-83 MODEL-B
@@ -143,7 +148,7 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
             bar_sync(kBFull + b);
             if (r >= 2u) bar_sync(kFEmpty + b);
             if (full) {
-#pragma unroll 8
+#pragma unroll kCoderUnroll
                 for (uint32_t j = 0; j < kRound; ++j) {
                     const uint32_t m = __shfl_sync(kFull, m_l, j);
                     const uint32_t pa = sm.ring_a[b][j][lane], pb = sm.ring_b[b][j][lane];
