@@ -74,7 +74,18 @@ size_t index_scratch_bytes(size_t c) { return make_plan(c).total; }
 
 __device__ __forceinline__ uint32_t ld16(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
 
-// ---- 1. mark: thread = 32 consecutive offsets = one bitmap word
+// ---- 1. mark: thread = 32 consecutive offsets = one bitmap word.
+// Prefilter first, branch free: away from the end of the stream only rawLen == packet can start
+// a packet, i.e. the two bytes at o+2 (one funnel shift + compare per offset, ~1 in 65536
+// random offsets pass); the full test runs only on the survivors.  Within packet+512 bytes of
+// the end every offset gets the full test (the last packet may be short).
+__device__ __forceinline__ bool index_is_candidate(const uint8_t *__restrict__ payload, size_t o, size_t c, uint32_t packet)
+{
+    const uint32_t len = ld16(payload + o), raw = ld16(payload + o + 2);
+    return len > kHdr && len <= packet + 512u && o + len <= c &&
+           (raw == packet || (o + len == c && raw >= 1u && raw <= packet));
+}
+
 __global__ void __launch_bounds__(kMarkThreads)
 index_mark_kernel(const uint8_t *__restrict__ payload, size_t c, uint32_t *__restrict__ bitmap, size_t words,
                   uint32_t packet)
@@ -82,21 +93,27 @@ index_mark_kernel(const uint8_t *__restrict__ payload, size_t c, uint32_t *__res
     const size_t w = (size_t)blockIdx.x * kMarkThreads + threadIdx.x;
     if (w >= words) return;
     const size_t o0 = w * 32;
-    // bytes o0 .. o0+34 (payload is readable GPUAR_PAD_BYTES past c; base is 16-byte aligned)
-    const uint4 *v = reinterpret_cast<const uint4 *>(payload + o0);
-    const uint4 a = v[0], b = v[1];
-    const uint32_t tail = *reinterpret_cast<const uint32_t *>(payload + o0 + 32);
-    const uint32_t x[9] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, tail};
-    uint32_t bits = 0;
+    uint32_t pre = 0xFFFFFFFFu;
+    if (o0 + 32u + packet + 512u < c) {
+        // bytes o0 .. o0+35 (payload is readable GPUAR_PAD_BYTES past c; base is 16-byte aligned)
+        const uint4 *v = reinterpret_cast<const uint4 *>(payload + o0);
+        const uint4 a = v[0], b = v[1];
+        const uint32_t tail = *reinterpret_cast<const uint32_t *>(payload + o0 + 32);
+        const uint32_t x[10] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, tail, 0u};   // x[9] only pads the funnel
+        pre = 0;
 #pragma unroll
-    for (uint32_t j = 0; j < 32; ++j) {
-        const uint32_t q = j >> 2, s = (j & 3u) * 8u;
-        const uint32_t four = __funnelshift_r(x[q], x[q + 1], s);   // bytes o..o+3
-        const uint32_t len = four & 0xFFFFu, raw = four >> 16;
+        for (uint32_t j = 0; j < 32; ++j) {
+            const uint32_t k = j + 2u;                              // rawLen lives at bytes o+2, o+3
+            const uint32_t two = __funnelshift_r(x[k >> 2], x[(k >> 2) + 1u], (k & 3u) * 8u) & 0xFFFFu;
+            pre |= (uint32_t)(two == packet) << j;
+        }
+    }
+    uint32_t bits = 0;
+    while (pre) {
+        const uint32_t j = __ffs(pre) - 1u;
+        pre &= pre - 1u;
         const size_t o = o0 + j;
-        bool ok = len > kHdr && len <= packet + 512u && o + len <= c;
-        ok = ok && (raw == packet || (o + len == c && raw >= 1u && raw <= packet));
-        bits |= (uint32_t)ok << j;
+        if (o + kHdr <= c && index_is_candidate(payload, o, c, packet)) bits |= 1u << j;
     }
     bitmap[w] = bits;
 }
