@@ -302,3 +302,51 @@ def test_beyond_4gib_header_and_round_trip(dev, codec):
     # prefix property: the first 1 MiB of the payload is the golden payload of mixed(31, 1 MiB)
     head = O.encode(D.mixed(31, 1 << 20))
     assert np.array_equal(payload[: head.size].cpu().numpy(), head)
+
+
+def test_corrupt_streams_never_fault(dev, codec):
+    """Robustness the reference lacks (it may read out of bounds on corrupt input,
+    gpuar_kernel.cu:746): damaged bitstreams decode to garbage of the right length, damaged chains are
+    reported, and the device stays healthy."""
+    from gpuar_b200._lib import GpuarError
+    rng = np.random.default_rng(11)
+    data = D.mixed(5, 8192 * 40 + 100)
+    pay = O.encode(data)
+    offs = O.index(pay).astype(np.int64)
+    for trial in range(20):
+        bad = pay.copy()
+        hits = rng.integers(0, bad.size, size=8)
+        hits = np.array([h for h in hits if not np.any((h >= offs) & (h < offs + 4))], dtype=np.int64)  # keep headers intact
+        bad[hits] ^= rng.integers(1, 256, size=hits.size).astype(np.uint8)
+        out = dev.decode_bytes(to_dev(bad)).cpu().numpy()
+        assert out.size == data.size
+    for trial in range(20):
+        bad = pay.copy()
+        o = int(offs[rng.integers(0, offs.size)])
+        bad[o + rng.integers(0, 4)] ^= np.uint8(1 << rng.integers(0, 8))
+        try:
+            out = dev.decode_bytes(to_dev(bad)).cpu().numpy()
+            assert out.size <= data.size + 8192
+        except GpuarError:
+            pass
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.decode_bytes(to_dev(pay)).cpu().numpy(), data)      # the device is still fine
+
+
+def test_abi_rejects_bad_arguments(dev, codec):
+    from gpuar_b200 import _lib
+    L = _lib.lib()
+    x = torch.zeros(8192 * 2 + 16, dtype=torch.uint8, device="cuda")
+    pay = torch.zeros(codec.payload_bound(8192 * 2) + 16, dtype=torch.uint8, device="cuda")
+    tot = torch.zeros(1, dtype=torch.int64, device="cuda")
+    scr = torch.zeros(int(L.gpuar_b200_encode_scratch_bytes(8192 * 2)) + 256, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ok = L.gpuar_b200_encode(x.data_ptr(), 8192 * 2, pay.data_ptr(), pay.numel(), tot.data_ptr(), None, scr.data_ptr(), scr.numel(), st)
+    assert ok == 0
+    # misaligned input, short payload buffer, short scratch, bad packet size
+    assert L.gpuar_b200_encode(x.data_ptr() + 1, 8192, pay.data_ptr(), pay.numel(), tot.data_ptr(), None, scr.data_ptr(), scr.numel(), st) == _lib.E_ARG
+    assert L.gpuar_b200_encode(x.data_ptr(), 8192 * 2, pay.data_ptr(), 100, tot.data_ptr(), None, scr.data_ptr(), scr.numel(), st) == _lib.E_ARG
+    assert L.gpuar_b200_encode(x.data_ptr(), 8192 * 2, pay.data_ptr(), pay.numel(), tot.data_ptr(), None, scr.data_ptr(), 16, st) == _lib.E_ARG
+    assert L.gpuar_b200_encode_ex(x.data_ptr(), 8192, 8200, pay.data_ptr(), pay.numel(), tot.data_ptr(), None, scr.data_ptr(), scr.numel(), st) == _lib.E_ARG
+    assert L.gpuar_b200_payload_bound_ex(8192, 20000) == 0
+    torch.cuda.synchronize()
