@@ -99,14 +99,16 @@ struct DeviceBuf {
         return e;
     }
 };
-constexpr int kLanes = 3;                        // chunks in flight in compress_host
+constexpr int kLanes = 8;                        // chunks in flight in the host-buffer pipelines
 struct HostPath {
     int device = -1;
     cudaStream_t stream[kLanes] = {}, copy = nullptr;
     cudaEvent_t done[kLanes] = {}, ready = nullptr;
     DeviceBuf in[kLanes], pay[kLanes], scratch[kLanes];
     DeviceBuf big_in, big_out, big_scratch, offsets, result;
-    uint64_t *h_total = nullptr;                 // pinned: per-lane payload totals + index result
+    uint64_t *h_total = nullptr;                 // pinned: per-lane payload totals
+    uint64_t *h_offsets = nullptr;               // pinned: packet offsets found by the host chain walk
+    size_t h_offsets_cap = 0;
 };
 static std::mutex g_mu;
 static std::vector<HostPath *> g_paths;
@@ -126,7 +128,7 @@ static int host_path(HostPath **out)
     }
     if ((e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking)) != cudaSuccess) return ck(e);
     if ((e = cudaEventCreateWithFlags(&h->ready, cudaEventDisableTiming)) != cudaSuccess) return ck(e);
-    if ((e = cudaMallocHost(&h->h_total, 16 * sizeof(uint64_t))) != cudaSuccess) return ck(e);
+    if ((e = cudaMallocHost(&h->h_total, (kLanes + 8) * sizeof(uint64_t))) != cudaSuccess) return ck(e);
     g_paths.push_back(h);
     *out = h;
     return 0;
@@ -335,12 +337,15 @@ int gpuar_b200_compress_host(const uint8_t *in, size_t n, uint8_t *gip, size_t g
     if (rc) return rc;
 
     // chunks rotate over kLanes streams: H2D, encode and scan+compact of chunk k overlap the D2H
-    // of chunk k-1; the host only waits for the 8-byte total of a chunk to know where the next
-    // one lands in the image.  A chunk's kernels take about the same time from 1 to ~20 000
-    // packets (a packet is a serial chain), so small inputs use 16 MiB chunks to start the
-    // pipeline early and large ones 64 MiB chunks to keep enough packets in flight.
-    size_t chunk = align_up(n / 8 + 1, kPacket);
-    chunk = chunk < ((size_t)16 << 20) ? ((size_t)16 << 20) : chunk > ((size_t)64 << 20) ? ((size_t)64 << 20) : chunk;
+    // of earlier chunks; the host only waits for the 8-byte total of a chunk to know where the
+    // next one lands in the image.  A chunk's kernels take about the same time from 1 to ~20 000
+    // packets (a packet is a serial chain of 8192 steps), so the end-to-end time is roughly
+    // H2D(everything) + one kernel latency + D2H(last chunk): small inputs use many small chunks
+    // to shorten that tail, large ones 64 MiB chunks to keep enough packets in flight.
+    // No more chunks than lanes while the input is small: a lane is only reused after its chunk
+    // has finished, which would stall the H2D stream for a kernel latency.
+    size_t chunk = align_up(n / kLanes + 1, kPacket);
+    chunk = chunk < ((size_t)4 << 20) ? ((size_t)4 << 20) : chunk > ((size_t)64 << 20) ? ((size_t)64 << 20) : chunk;
     const size_t chunks = (n + chunk - 1) / chunk;
     size_t pos = GPUAR_FILE_HEADER;
     cudaError_t e = cudaSuccess;
@@ -394,53 +399,77 @@ int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *ou
     std::lock_guard<std::mutex> lock(g_mu);
     HostPath *h = nullptr;
     if ((rc = host_path(&h))) return rc;
+    const uint8_t *pay = gip + GPUAR_FILE_HEADER;
 
-    // the header's size field is 32 bit in reference-written files; the chain is the truth.
-    // Upper bound on packets for buffer sizing: the caller's buffer.
-    const size_t max_packets = out_cap / kPacket + 1;
+    // The payload is in host memory, so the packet chain is walked here, one u16 per packet, as
+    // the reference's host driver does while it reads the file (gpu_compressor.cpp:294-320) -- but
+    // only to cut the stream into chunks of whole packets that flow through kLanes streams:
+    // H2D(chunk k+1) | decode(chunk k) | D2H(chunk k-1).  (Device-resident callers use
+    // gpuar_b200_index, the parallel chain discovery on the device.)  A decode launch takes about
+    // the same time from 1 packet to a full wave, so the end-to-end time is roughly
+    // H2D(everything) + one decode latency + D2H(last chunk).
     cudaError_t e = h->big_in.need(align_up(c, 16) + GPUAR_PAD_BYTES + 16);
-    if (e == cudaSuccess) e = h->big_scratch.need(index_scratch_bytes(c));
-    if (e == cudaSuccess) e = h->offsets.need(max_packets * 8);
-    if (e == cudaSuccess) e = h->result.need(64);
-    if (e == cudaSuccess) e = h->big_out.need(max_packets * (size_t)kPacket);
     if (e != cudaSuccess) return ck(e);
-    cudaStream_t st = h->stream[0];
     uint8_t *d_pay = (uint8_t *)h->big_in.p;
-    e = cudaMemsetAsync(d_pay + c, 0, GPUAR_PAD_BYTES, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_pay, gip + GPUAR_FILE_HEADER, c, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return ck(e);
-    rc = gpuar_b200_index(d_pay, c, (uint64_t *)h->offsets.p, max_packets, (uint64_t *)h->result.p,
-                          h->big_scratch.p, h->big_scratch.cap, st);
-    if (rc) return rc;
-    uint64_t *res = h->h_total + 8;
-    e = cudaMemcpyAsync(res, h->result.p, 32, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return ck(e);
-    if (res[2] != 0) return (int)(int64_t)res[2];
-    const size_t packets = (size_t)res[0], total = (size_t)res[1];
-    if ((uint32_t)raw != (uint32_t)total) return GPUAR_E_FORMAT;    // header field, file_header.hpp:61-66
-    if (total > out_cap || !out) return GPUAR_E_ARG;
+    size_t chunk_bytes = c / kLanes + 1;                             // payload bytes per chunk, before rounding to packets
+    if (chunk_bytes < ((size_t)2 << 20)) chunk_bytes = (size_t)2 << 20;
+    if (chunk_bytes > ((size_t)256 << 20)) chunk_bytes = (size_t)256 << 20;
 
-    // decode in packet ranges; the D2H of range k overlaps the decode of range k+1.  A range is one
-    // resident wave of the decode kernel (10 lane=packet warps per SM): anything smaller takes just
-    // as long, because a packet is a serial chain.
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    const size_t step = (size_t)sms * 10 * 32;                      // packets per range (370 MiB on B200)
-    for (size_t p0 = 0, k = 0; p0 < packets; p0 += step, ++k) {
-        const size_t m = (packets - p0 < step) ? packets - p0 : step;
+    const size_t max_packets = out_cap / kPacket + 2;
+    if (h->h_offsets_cap < max_packets) {
+        if (h->h_offsets) cudaFreeHost(h->h_offsets);
+        h->h_offsets = nullptr;
+        h->h_offsets_cap = 0;
+        if ((e = cudaMallocHost(&h->h_offsets, max_packets * sizeof(uint64_t))) != cudaSuccess) return ck(e);
+        h->h_offsets_cap = max_packets;
+    }
+    if ((e = h->offsets.need(max_packets * sizeof(uint64_t))) != cudaSuccess) return ck(e);
+    if ((e = h->big_out.need(max_packets * (size_t)kPacket)) != cudaSuccess) return ck(e);
+    if ((e = cudaMemsetAsync(d_pay + c, 0, GPUAR_PAD_BYTES, h->stream[0])) != cudaSuccess) return ck(e);
+    if ((e = cudaEventRecord(h->ready, h->stream[0])) != cudaSuccess) return ck(e);
+
+    size_t pos = 0, packets = 0, total = 0, lane = 0;
+    int status = 0;
+    while (pos < c && status == 0) {
+        // one chunk: whole packets until chunk_bytes of payload
+        const size_t p0 = packets, a = pos;
+        while (pos < c && pos - a < chunk_bytes) {
+            if (c - pos < kHdr) { status = GPUAR_E_FORMAT; break; }
+            const size_t len = (size_t)pay[pos] | ((size_t)pay[pos + 1] << 8);
+            const size_t r = (size_t)pay[pos + 2] | ((size_t)pay[pos + 3] << 8);
+            if (len <= kHdr || len > c - pos) { status = GPUAR_E_FORMAT; break; }
+            if (r == 0 || r > kPacket || (r != kPacket && pos + len != c)) { status = GPUAR_E_UNSUPPORTED; break; }
+            if (packets >= max_packets || total + r > out_cap || !out) { status = GPUAR_E_ARG; break; }
+            h->h_offsets[packets++] = pos;
+            total += r;
+            pos += len;
+        }
+        if (status) break;
+        const size_t m = packets - p0;
+        if (!m) break;
+        cudaStream_t st = h->stream[lane % kLanes];
+        ++lane;
+        if (lane == 1) e = cudaSuccess; else e = cudaStreamWaitEvent(st, h->ready, 0);   // padding is in place
+        // H2D of this chunk's bytes (rounded out to 16) and of its offsets, decode, D2H
+        const size_t a16 = a & ~(size_t)15, b16 = align_up(pos, 16) < c ? align_up(pos, 16) : c;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_pay + a16, pay + a16, b16 - a16, cudaMemcpyHostToDevice, st);
+        uint64_t *d_off = (uint64_t *)h->offsets.p + p0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, h->h_offsets + p0, m * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return ck(e);
         uint8_t *d_out = (uint8_t *)h->big_out.p + p0 * kPacket;
-        rc = gpuar_b200_decode(d_pay, c, (const uint64_t *)h->offsets.p + p0, m, d_out, m * (size_t)kPacket, st);
+        rc = gpuar_b200_decode(d_pay, c, d_off, m, d_out, m * (size_t)kPacket, st);
         if (rc) return rc;
-        e = cudaEventRecord(h->ready, st);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->copy, h->ready, 0);
         const size_t lo = p0 * kPacket, hi = (lo + m * kPacket < total) ? lo + m * kPacket : total;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out + lo, d_out, hi - lo, cudaMemcpyDeviceToHost, h->copy);
+        e = cudaMemcpyAsync(out + lo, d_out, hi - lo, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return ck(e);
     }
-    e = cudaStreamSynchronize(h->copy);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    for (int l = 0; l < kLanes; ++l) {
+        cudaError_t es = cudaStreamSynchronize(h->stream[l]);
+        if (e == cudaSuccess) e = es;
+    }
+    if (status) return status;
     if (e != cudaSuccess) return ck(e);
+    if ((uint32_t)raw != (uint32_t)total) return GPUAR_E_FORMAT;    // header field, file_header.hpp:61-66
     *out_bytes = total;
     return 0;
 }

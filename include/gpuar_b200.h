@@ -110,8 +110,11 @@ int gpuar_b200_decode_ex(const uint8_t *d_payload, size_t c, size_t packet_bytes
 
 /* ------------------------------------------------- host-buffer entry points
  * Whole .gip image in host memory <-> raw bytes in host memory on the current
- * device: staging, H2D, kernels, D2H, header.  Synchronous.  What a caller of
- * the reference's GPUCompressor::compress/decompress gets, minus the file I/O.
+ * device: staging, H2D, kernels, D2H, header, pipelined in chunks over several
+ * streams.  Synchronous.  What a caller of the reference's
+ * GPUCompressor::compress/decompress gets, minus the file I/O.  decompress_host
+ * hops over the compLen fields on the host (the image is in host memory anyway,
+ * cf. gpu_compressor.cpp:294-320) only to cut it into chunks of whole packets.
  * `gip_cap` >= 20 + gpuar_b200_payload_bound(n).
  */
 int gpuar_b200_compress_host(const uint8_t *in, size_t n, uint8_t *gip, size_t gip_cap, size_t *gip_bytes);
