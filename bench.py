@@ -41,6 +41,11 @@ WORKLOADS = {
     "s1g": ("and3", 2, 1 << 30, "and3(2, 1 GiB) low-entropy (BASELINE config 3)"),
     "m2g": ("mixed", 3, 2 << 30, "mixed(3, 2 GiB per rank) (BASELINE config 4 shard)"),
     "m4g": ("mixed", 7, 4 << 30, "mixed(7, 4 GiB) (BASELINE config 5)"),
+    # tuning only (where the warp-specialised encoder hands over to the lane=packet one)
+    "u128m": ("uniform", 0x65, 128 << 20, "uniform(0x65, 128 MiB) (tuning)"),
+    "u192m": ("uniform", 0x66, 192 << 20, "uniform(0x66, 192 MiB) (tuning)"),
+    "u256m": ("uniform", 0x67, 256 << 20, "uniform(0x67, 256 MiB) (tuning)"),
+    "u384m": ("uniform", 0x68, 384 << 20, "uniform(0x68, 384 MiB) (tuning)"),
 }
 
 
@@ -258,6 +263,8 @@ def run_ours(args):
             os.close(saved)
     dev = codec.DeviceCodec(local)
     _lib.set_option(_lib.OPT_ENCODE_PATH, {"auto": 0, "fused": 1, "ws": 2}[args.encode_path])
+    if args.work_unit:
+        _lib.set_option(_lib.OPT_COMPACT_TILE, args.work_unit)
     sharded = ShardedCodec(dev, rank, world, "segments")
     gathered = ShardedCodec(dev, rank, world, "gather") if world > 1 else None
 
@@ -398,7 +405,7 @@ def run_ours(args):
             "config": {"workload": args.workload, "desc": desc, "bytes_per_rank": nbytes, "packet_bytes": packet,
                        "payload_bytes_rank0": c, "l2": "flushed between timed iterations (256 MiB write)",
                        "parallelism": f"packet-range shards x{world}" if world > 1 else "single GPU",
-                       "encode_path": args.encode_path},
+                       "encode_path": args.encode_path, "work_unit_packets": args.work_unit or "auto"},
             "encode_shards_in_place": {"value": job / (t_local / args.steps) / GB, "unit": "GB/s",
                                        "note": "encode only, every shard's payload left on its own GPU (SURVEY 8e)"},
             "encode_gather_one_gpu": {"value": job / (t_gather / args.steps) / GB, "unit": "GB/s",
@@ -449,6 +456,9 @@ def main():
                          "4096/12288/16112 for the BASELINE config-5 sweep; e2e and CPU baseline stay at 8192)")
     ap.add_argument("--encode-path", default="auto", choices=["auto", "fused", "ws"],
                     help="encoder kernel: auto (by packet count), fused lane=packet, warp-specialised")
+    ap.add_argument("--work-unit", type=int, default=0,
+                    help="packets per CTA of the scan + compaction kernel (0 = auto; 4..128 = 32 KiB..1 MiB of "
+                         "input: the work-unit half of the BASELINE config-5 sweep)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -101,7 +101,7 @@ def check(code: int, what: str) -> None:
         raise GpuarError(code, what)
 
 
-OPT_ENCODE_PATH, OPT_WS_MAX_PACKETS = 1, 2
+OPT_ENCODE_PATH, OPT_WS_MAX_PACKETS, OPT_COMPACT_TILE = 1, 2, 3
 ENCODE_AUTO, ENCODE_FUSED, ENCODE_WS = 0, 1, 2
 
 

@@ -42,7 +42,7 @@ static int ck(cudaError_t e) { return (int)e; }
 // ---- tuning knobs (gpuar_b200_set_option)
 static int g_encode_path = 0;                    // 0 auto, 1 fused lane=packet, 2 warp-specialised
 // auto: the warp-specialised kernel while the input is at most one resident wave of its CTAs
-static size_t g_ws_max_packets = (size_t)148 * 5 * 32;
+static size_t g_ws_max_packets = (size_t)148 * 3 * 32;   // three 62.6 KB CTAs fit one SM: one resident wave
 
 static cudaError_t encode_slots(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t stride, uint32_t *d_sizes,
                                 uint32_t packet, cudaStream_t st)
@@ -266,6 +266,9 @@ int gpuar_b200_set_option(int key, long long value)
     case GPUAR_OPT_WS_MAX_PACKETS:
         if (value < 0) return GPUAR_E_ARG;
         g_ws_max_packets = (size_t)value;
+        return 0;
+    case GPUAR_OPT_COMPACT_TILE:
+        if (value < 0 || value > 128 || !set_compact_tile((uint32_t)value)) return GPUAR_E_ARG;
         return 0;
     default:
         return GPUAR_E_ARG;

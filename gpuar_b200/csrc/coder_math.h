@@ -10,6 +10,7 @@
 //   range = upper - lower + 1 = 65536 - V - L                   (> 2^14 between symbols)
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define GPUAR_HD __host__ __device__ __forceinline__
@@ -72,6 +73,13 @@ GPUAR_HD uint32_t div_total(uint32_t n, uint32_t m, uint32_t sh) { return mulhi3
 //        U1 = upper bound before renormalisation (its top k bits are the output bits)
 // Reference loop in closed form: always k matching-MSB shifts, then u underflow shifts, and
 // L = (L1 << (k+u)) & 0x7FFF, V = (V1 << (k+u)) & 0x7FFF.
+GPUAR_HD void shifts_of(uint32_t L1, uint32_t U1, uint32_t &k, uint32_t &u)
+{
+    k = clz32((L1 ^ U1) & 0xFFFFu) - 16u;
+    const uint32_t g = (L1 & ~U1) << k;              // positions with L=1, U=0 after the k shifts
+    u = clz32(~g & 0x7FFFu) - 17u;                   // run of them starting at bit 14
+}
+
 GPUAR_HD void narrow_renorm(uint32_t &L, uint32_t &V, uint32_t lo, uint32_t hi, uint32_t m, uint32_t sh,
                             uint32_t &k, uint32_t &u, uint32_t &U1)
 {
@@ -81,13 +89,138 @@ GPUAR_HD void narrow_renorm(uint32_t &L, uint32_t &V, uint32_t lo, uint32_t hi, 
     const uint32_t V1 = 65536u - L - qa;             // 0xFFFF - (L + qa - 1)
     const uint32_t L1 = L + qb;
     U1 = V1 ^ 0xFFFFu;
-    k = clz32((L1 ^ U1) & 0xFFFFu) - 16u;
-    const uint32_t g = (L1 & V1) << k;               // positions with L=1, U=0 after the k shifts
-    u = clz32(~g & 0x7FFFu) - 17u;                   // run of them starting at bit 14
+    shifts_of(L1, U1, k, u);
     const uint32_t t = k + u;
     L = (L1 << t) & 0x7FFFu;
     V = (V1 << t) & 0x7FFFu;
 }
+
+// ---- the same step with a single normalisation on the dependent chain.
+// State here is (L, R) with R = range = upper - lower + 1 carried explicitly.  The recurrence
+// only needs the TOTAL shift t = k + u, and t follows from the WIDTH W = U1 - L1 + 1 of the
+// narrowed interval up to one position: the renormalised width W * 2^t lies in (2^14, 2^16],
+// so with e = floor(log2(W - 1)) (e = -1 for W = 1) t is 14 - e or 15 - e.  Shift by
+// s1 = 15 - e and look at the two top bit pairs of the 17-bit frame (L1 and U1 carry a
+// leading 0, so the inverted upper bound Vx carries a leading 1 -- s1 = 0 then falls out as
+// "MSBs equal"): the last shift is due exactly when the MSBs (bit 16) are equal, or the next
+// bits (bit 15) read L = 1, U = 0 (underflow).  Otherwise one shift less.  Every shift
+// doubles the width exactly, so R = W << t needs neither L nor the upper bound.
+//
+// e comes from the exponent of a float, built with one integer add and one float subtract,
+// so no count-leading-zeros or conversion instruction -- both variable-latency on the XU
+// pipe -- sits on the chain: 0x4BFFFFFF + W are the bits of 2^25 + 4(W - 1) (exact, ulp 4),
+// and subtracting 2^25 - 2 leaves 4W - 2 = 4 (W - 0.5) exactly, whose biased exponent is
+// E = 129 + e.  E is congruent to e + 1 = 16 - s1 modulo 32, so "<< s1" is a funnel shift
+// RIGHT of the operand pre-shifted by 16 with E itself as the (wrapping) shift amount.
+// k and u individually matter only for the emitted bits; the encoder derives them off the
+// chain (shifts_of).
+GPUAR_HD uint32_t width_exponent(uint32_t qa, uint32_t qb)    // 129 + floor(log2(qa - qb - 1)); 128 for qa - qb = 1
+{
+    float f;
+#if defined(__CUDA_ARCH__)
+    uint32_t b;                                               // one three-input add
+    asm("{\n\t.reg .u32 t;\n\tsub.u32 t, %1, %2;\n\tadd.u32 %0, t, 0x4BFFFFFF;\n\t}" : "=r"(b) : "r"(qa), "r"(qb));
+    f = __uint_as_float(b) - 33554430.0f;
+    return __float_as_uint(f) >> 23;
+#else
+    const uint32_t b = 0x4BFFFFFFu + (qa - qb);
+    memcpy(&f, &b, 4);
+    f -= 33554430.0f;
+    uint32_t r;
+    memcpy(&r, &f, 4);
+    return r >> 23;
+#endif
+}
+GPUAR_HD uint32_t funnel_r_wrap(uint32_t lo, uint32_t hi, uint32_t s)    // low 32 bits of {hi:lo} >> (s mod 32)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> (s & 31u));
+#endif
+}
+// x >> 1 that the compiler may not fold into the select that follows it: both candidates of
+// narrow_total must exist BEFORE the decision, or they land back on the dependent chain.
+GPUAR_HD uint32_t half_eager(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm volatile("shr.b32 %0, %1, 1;" : "=r"(r) : "r"(x));
+    return r;
+#else
+    return x >> 1;
+#endif
+}
+GPUAR_HD bool last_shift_due(uint32_t A, uint32_t B)          // MSBs (bit 16) equal, or bit 15: L = 1, U = 0
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t x, y;
+    asm("lop3.b32 %0, %1, %2, 0x10000, 0x28;" : "=r"(x) : "r"(A), "r"(B));   // (A ^ B) & bit 16
+    asm("lop3.b32 %0, %1, %2, 0x8000, 0x80;" : "=r"(y) : "r"(A), "r"(B));    // A & B & bit 15
+    return (x | y) != 0u;
+#else
+    return (((A ^ B) & 0x10000u) | (A & B & 0x8000u)) != 0u;
+#endif
+}
+
+//   in : L, R; lo = cum[s], hi = cum[s+1]; (m, sh) for the current total
+//   out: L, R renormalised; L1 = lower bound and Vx = 0x1FFFF - upper bound before
+//        renormalisation; t = total shift (0..16); As = L1 << t with bit 15 kept
+//        (bit 15 set <=> u != 0)
+GPUAR_HD void narrow_total(uint32_t &L, uint32_t &R, uint32_t lo, uint32_t hi, uint32_t m, uint32_t sh,
+                           uint32_t &L1, uint32_t &Vx, uint32_t &t, uint32_t &As)
+{
+    const uint32_t qa = div_total(hi * R, m, sh);
+    const uint32_t qb = div_total(lo * R, m, sh);
+    const uint32_t E = width_exponent(qa, qb);                // = 16 - s1 (mod 32)
+    L1 = L + qb;
+    Vx = 0x20000u - L - qa;                                   // bit 16 always set
+    const uint32_t A = funnel_r_wrap(L1 << 16, 0u, E);        // L1 << s1
+    const uint32_t B = funnel_r_wrap(Vx << 16, 1u, E);        // Vx << s1
+    const uint32_t R1 = funnel_r_wrap((qa - qb) << 16, 0u, E);
+    const uint32_t R0 = half_eager(R1), A0 = half_eager(A);
+    const bool last = last_shift_due(A, B);
+    R = last ? R1 : R0;
+    As = last ? A : A0;
+    L = As & 0x7FFFu;
+    t = (last ? 16u : 15u) - (E & 31u);
+}
+
+// The encoder's CODER warp goes one step further and never applies the decision to the
+// range at all: it carries R1 = W << s1 (always in (2^15, 2^16]) together with the pending
+// halving sx = 1 - last, and the next step divides with sx added to the shift of the
+// reciprocal division: floor(c * (R1 >> sx) / T) = floor(floor(c * R1 / T) >> sx), R1 being
+// even whenever sx = 1.  The products and the multiply-high of the next step then start from
+// R1 directly, in parallel with the decision, and the decision itself is integer arithmetic
+// (no predicate, whose write-to-use latency is several times that of a register).
+//   state: L (15 bit), R1, sx;  true range = R1 >> sx.   Start: L = 0, R1 = 65536, sx = 0.
+GPUAR_HD void narrow_lazy(uint32_t &L, uint32_t &R1, uint32_t &sx, uint32_t lo, uint32_t hi, uint32_t m,
+                          uint32_t sh, uint32_t &L1, uint32_t &Vx)
+{
+    const uint32_t qa = (mulhi32(hi * R1, m) >> sh) >> sx;
+    const uint32_t qb = (mulhi32(lo * R1, m) >> sh) >> sx;
+    const uint32_t E = width_exponent(qa, qb);
+    L1 = L + qb;
+    Vx = 0x20000u - L - qa;
+    const uint32_t A = funnel_r_wrap(L1 << 16, 0u, E), B = funnel_r_wrap(Vx << 16, 1u, E);      // << s1
+    const uint32_t A0 = funnel_r_wrap(L1 << 15, 0u, E), B0 = funnel_r_wrap(Vx << 15, 0u, E);    // << (s1 - 1)
+    R1 = funnel_r_wrap((qa - qb) << 16, 0u, E);
+    // bit 15 of the half frame = bit 16 of the full one: MSBs equal <=> L and inverted U differ there
+#if defined(__CUDA_ARCH__)
+    uint32_t x, y, nz;                                        // three-input logic ops, two levels
+    asm("lop3.b32 %0, %1, %2, 0x8000, 0x28;" : "=r"(x) : "r"(A0), "r"(B0));       // (A0 ^ B0) & bit 15
+    asm("lop3.b32 %0, %1, %2, 0x8000, 0x80;" : "=r"(y) : "r"(A), "r"(B));         // A & B & bit 15
+    asm("lop3.b32 %0, %1, %2, 0x8000, 0x56;" : "=r"(nz) : "r"(x), "r"(y));        // (x | y) ^ bit 15
+    sx = nz >> 15;
+#else
+    sx = ((((A0 ^ B0) & 0x8000u) | (A & B & 0x8000u)) ^ 0x8000u) >> 15;
+#endif
+    L = (A >> sx) & 0x7FFFu;
+}
+
+// L1 | U1 << 16 from L1 and Vx = 0x1FFFF - U1 (bit 16 set), as two multiply-adds:
+// U1 << 16 = -(Vx + 1) << 16 modulo 2^32.
+GPUAR_HD uint32_t pack_bounds(uint32_t L1, uint32_t Vx) { return Vx * 0xFFFF0000u + (L1 - 0x10000u); }
 
 // ---- encoder bit sink: MSB-first stream (gpuar_kernel.cu:128-151), flushed as 32-bit words.
 // Branch free: after appending, at most one whole word is ready; it is stored under a
@@ -157,6 +290,60 @@ GPUAR_HD void emit_symbol(BitSink &out, uint32_t &pend, uint32_t k, uint32_t u, 
     else emit_field(out, pend, k, u, U1);
 }
 
+// The same emission from a two-word descriptor, so that a warp other than the one that owns
+// the bit sink can do everything that does not depend on `pend` (encode_ws.cu, FIELD -> BITS).
+// The fields sit where the consumer gets each of them with one instruction (mask of the low
+// bits, plain shift from the top, or a wrapping shift amount that ignores the bits above it):
+//   w0: bits 0-4 k | 5-9 max(k,1)-1 | 10 valid | 28-31 u
+//   w1: bits 0-14 the k-1 bits after the first | 31 the first bit, inverted
+// The producer builds them with multiply-adds where the fields cannot overlap (FMA pipe; the
+// integer ALU pipe is the one these kernels saturate).
+struct FieldDesc { uint32_t w0, w1; };
+
+GPUAR_HD FieldDesc pack_field(uint32_t k, uint32_t u, uint32_t c)       // c = L1 | U1 << 16
+{
+    const uint32_t U1 = c >> 16;
+    const uint32_t km1 = k ? k - 1u : 0u;
+    const uint32_t rest = (U1 >> (16u - k)) & ~(0xFFFFFFFFu << km1);
+    FieldDesc d;
+    d.w0 = (u << 28) + (km1 * 32u + k) + 1024u;
+    d.w1 = rest | (~c & 0x80000000u);
+    return d;
+}
+
+GPUAR_HD uint32_t shl_wrap(uint32_t x, uint32_t s)            // x << (s mod 32)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(0u, x, s);
+#else
+    return x << (s & 31u);
+#endif
+}
+
+GPUAR_HD void emit_packed(BitSink &out, uint32_t &pend, FieldDesc d)        // requires !emit_is_long(pend, k)
+{
+    const uint32_t k = d.w0 & 31u, u = d.w0 >> 28;
+    const uint32_t head = (1u << (pend & 31u)) - (d.w1 >> 31);
+    const uint32_t val = shl_wrap(head, d.w0 >> 5) | (d.w1 & 0x7FFFu);
+    out.put(k ? val : 0u, k ? k + pend : 0u);
+    pend = k ? u : pend + u;
+}
+
+GPUAR_HD void emit_packed_any(BitSink &out, uint32_t &pend, FieldDesc d)
+{
+    const uint32_t k = d.w0 & 31u;
+    if (emit_is_long(pend, k)) {
+        const uint32_t nb = d.w1 >> 31;
+        out.put(nb ^ 1u, 1u);
+        out = put_run(out, nb, pend);
+        out.put(d.w1 & 0x7FFFu, k - 1u);
+        pend = d.w0 >> 28;
+    } else {
+        emit_packed(out, pend, d);
+    }
+}
+GPUAR_HD bool field_valid(FieldDesc d) { return (d.w0 & 1024u) != 0u; }
+
 // End of packet: bit 14 of L, then pend+1 inverted copies (gpuar_kernel.cu:379-388); zero
 // padding to a byte (:430-439).  Writes the tail bytes and the 4-byte packet header (:525-528)
 // at `slot` (out.words == slot + 4).  Returns compLen.
@@ -197,11 +384,14 @@ GPUAR_HD uint32_t divide_exact(uint32_t num, uint32_t range)      // num < 2^30,
     return q;
 }
 
-GPUAR_HD uint32_t unscale(uint32_t code, uint32_t L, uint32_t V, uint32_t T)
+GPUAR_HD uint32_t unscale_range(uint32_t code, uint32_t L, uint32_t range, uint32_t T)
 {
-    const uint32_t range = 65536u - V - L;
     const uint32_t num = (((code - L) & 0xFFFFu) + 1u) * T - 1u;
     return divide_exact(num, range);
+}
+GPUAR_HD uint32_t unscale(uint32_t code, uint32_t L, uint32_t V, uint32_t T)
+{
+    return unscale_range(code, L, 65536u - V - L, T);
 }
 
 // byte permute of the 8 bytes {b:a} (prmt.b32, default mode).  Selector nibbles 0..7 pick a
@@ -297,10 +487,9 @@ GPUAR_HD uint32_t tree_decode(uint64_t &root, uint64_t *nodes, uint32_t stride, 
 // level-2 node loads are issued before `target` exists; the two lower levels then run on
 // `target` as in tree_decode.  Same result, the dependent chain is ~2 shared-memory round
 // trips shorter.  (t * range <= 8448 * 65536 < 2^30, num < 2^30: 32-bit compares are exact.)
-GPUAR_HD uint32_t tree_decode_early(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t code, uint32_t L,
-                                    uint32_t V, uint32_t T, uint32_t &lo, uint32_t &cnt)
+GPUAR_HD uint32_t tree_decode_early_range(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t code,
+                                          uint32_t L, uint32_t range, uint32_t T, uint32_t &lo, uint32_t &cnt)
 {
-    const uint32_t range = 65536u - V - L;
     const uint32_t num = (((code - L) & 0xFFFFu) + 1u) * T - 1u;
     // level 0
     const uint32_t r0 = (uint32_t)root, r1 = (uint32_t)(root >> 32);
@@ -341,6 +530,12 @@ GPUAR_HD uint32_t tree_decode_early(uint64_t &root, uint64_t *nodes, uint32_t st
     return idx;
 }
 
+GPUAR_HD uint32_t tree_decode_early(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t code, uint32_t L,
+                                    uint32_t V, uint32_t T, uint32_t &lo, uint32_t &cnt)
+{
+    return tree_decode_early_range(root, nodes, stride, code, L, 65536u - V - L, T, lo, cnt);
+}
+
 // Encoder side of the model (own tree, own leaf format).  The symbol is known, so the child
 // indices are its bit pairs and the node loads are independent of each other.
 //   levels 0-2: W-form nodes (0, t0, t1, t2) as in the decoder: slot c = count below child c;
@@ -359,7 +554,7 @@ GPUAR_HD void enc_tree_init(uint64_t &root, uint64_t *nodes, uint32_t stride)
     for (uint32_t q = 0; q < 64; ++q, ++n) nodes[n * stride] = enc_leaf_init();
 }
 
-GPUAR_HD uint32_t enc_upper(uint64_t &node, uint32_t c)          // slot c, then +1 on the slots above c
+GPUAR_HD uint32_t enc_upper(uint64_t &node, uint32_t c)   // slot c, then +1 above c
 {
     const uint32_t below = prmt((uint32_t)node, (uint32_t)(node >> 32), 0x0010u + 0x0022u * c);
     node += 0x0001000100010000ull << (16u * c);
@@ -369,14 +564,77 @@ GPUAR_HD uint32_t enc_upper(uint64_t &node, uint32_t c)          // slot c, then
 // The levels are independent of each other given the symbol, so the model can be split:
 // levels 0-1 (root + 4 nodes) and levels 2-3 (16 nodes + 64 leaves).  cum[s] is the sum
 // of the two partial results.
+GPUAR_HD uint32_t tree_encode_upper_at(uint64_t &root, uint64_t *node1, uint32_t c0, uint32_t c1)
+{
+    uint64_t n1 = *node1;
+    uint32_t acc = enc_upper(root, c0);
+    acc += enc_upper(n1, c1);
+    *node1 = n1;
+    return acc;
+}
 GPUAR_HD uint32_t tree_encode_upper(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t s)
 {
-    uint64_t *const p1 = nodes + (s >> 6) * stride;
-    uint64_t n1 = *p1;
-    uint32_t acc = enc_upper(root, s >> 6);
-    acc += enc_upper(n1, (s >> 4) & 3u);
-    *p1 = n1;
+    return tree_encode_upper_at(root, nodes + (s >> 6) * stride, s >> 6, (s >> 4) & 3u);
+}
+
+GPUAR_HD uint32_t tree_encode_mid_at(uint64_t *node2, uint32_t c)                      // level 2 alone
+{
+    uint64_t n2 = *node2;
+    const uint32_t acc = enc_upper(n2, c);
+    *node2 = n2;
     return acc;
+}
+GPUAR_HD uint32_t tree_encode_mid(uint64_t *nodes, uint32_t stride, uint32_t s)
+{
+    return tree_encode_mid_at(nodes + (4u + (s >> 4)) * stride, (s >> 2) & 3u);
+}
+
+GPUAR_HD uint32_t tree_encode_leaf_at(uint64_t *node3, uint32_t c, uint32_t &cnt)      // level 3 alone
+{
+    uint64_t n3 = *node3;
+    // prefix sums of the four plain counts in W-form, then the same permute
+    const uint32_t l = (uint32_t)n3, h = (uint32_t)(n3 >> 32);
+    const uint32_t x = l * 0x10001u;                               // (n0, n0+n1)
+    const uint32_t s01 = x >> 16;
+    const uint32_t s012 = s01 + (h & 0xFFFFu);
+    const uint32_t acc = prmt(x << 16, s01 | (s012 << 16), 0x0010u + 0x0022u * c);
+    cnt = prmt(l, h, 0x3210u + 0x2222u * c) & 0xFFFFu;
+    n3 += 1ull << (16u * c);
+    *node3 = n3;
+    return acc;
+}
+GPUAR_HD uint32_t tree_encode_leaf(uint64_t *nodes, uint32_t stride, uint32_t s, uint32_t &cnt)
+{
+    return tree_encode_leaf_at(nodes + (20u + (s >> 2)) * stride, s & 3u, cnt);
+}
+
+// Four symbols at a time (encode_ws.cu): the bit fields a level needs are masked for all four
+// bytes of an input word at once and picked per symbol with one byte permute, instead of a
+// shift-and-mask pair per field and symbol (the integer ALU pipe is what that kernel saturates).
+//   level 0-1: a = c0 of each byte, b = c1        level 2: a = (s >> 4) << 4, b = c2
+//   level 3  : a = (s >> 2) << 2,    b = c3
+struct WordFields { uint32_t a, b; };
+GPUAR_HD WordFields word_fields_upper(uint32_t w) { return {(w >> 6) & 0x03030303u, (w >> 4) & 0x03030303u}; }
+GPUAR_HD WordFields word_fields_mid(uint32_t w) { return {w & 0xF0F0F0F0u, (w >> 2) & 0x03030303u}; }
+GPUAR_HD WordFields word_fields_leaf(uint32_t w) { return {w & 0xFCFCFCFCu, w & 0x03030303u}; }
+GPUAR_HD uint32_t byte_of(uint32_t w, uint32_t j) { return prmt(w, 0u, 0x4440u + j); }   // byte j, zero extended
+
+GPUAR_HD uint64_t *byte_offset(uint64_t *p, uint32_t bytes)
+{
+    return reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(p) + bytes);
+}
+GPUAR_HD uint32_t tree_encode_upper_word(uint64_t &root, uint64_t *nodes, uint32_t stride, WordFields f, uint32_t j)
+{
+    const uint32_t c0 = byte_of(f.a, j);
+    return tree_encode_upper_at(root, byte_offset(nodes, c0 * stride * 8u), c0, byte_of(f.b, j));
+}
+GPUAR_HD uint32_t tree_encode_mid_word(uint64_t *nodes, uint32_t stride, WordFields f, uint32_t j)
+{
+    return tree_encode_mid_at(byte_offset(nodes + 4u * stride, (byte_of(f.a, j) * stride) >> 1), byte_of(f.b, j));
+}
+GPUAR_HD uint32_t tree_encode_leaf_word(uint64_t *nodes, uint32_t stride, WordFields f, uint32_t j, uint32_t &cnt)
+{
+    return tree_encode_leaf_at(byte_offset(nodes + 20u * stride, byte_of(f.a, j) * stride * 2u), byte_of(f.b, j), cnt);
 }
 
 GPUAR_HD uint32_t tree_encode_lower(uint64_t *nodes, uint32_t stride, uint32_t s, uint32_t &cnt)
@@ -463,6 +721,14 @@ GPUAR_HD uint32_t advance_code(uint32_t code, uint32_t k, uint32_t u, BitSource 
 {
     const uint32_t t = k + u;
     const uint32_t next = (funnel_l(in.hi, code, t) & 0xFFFFu) ^ (u ? 0x8000u : 0u);
+    in.skip(t);
+    return next;
+}
+
+// the same from narrow_total's outputs: t = k + u, and bit 15 of As says whether u != 0
+GPUAR_HD uint32_t advance_code_total(uint32_t code, uint32_t t, uint32_t As, BitSource &in)
+{
+    const uint32_t next = (funnel_l(in.hi, code, t) & 0xFFFFu) ^ (As & 0x8000u);
     in.skip(t);
     return next;
 }

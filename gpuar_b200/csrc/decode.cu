@@ -25,6 +25,12 @@
 #ifndef GPUAR_DEC_EARLY_BIG
 #define GPUAR_DEC_EARLY_BIG 0       // 1: multiplicative top levels also in the throughput variant
 #endif
+#ifndef GPUAR_DEC_TOTAL_SMALL
+#define GPUAR_DEC_TOTAL_SMALL 1     // 1: single-normalisation step (narrow_total) in the latency variant
+#endif
+#ifndef GPUAR_DEC_TOTAL_BIG
+#define GPUAR_DEC_TOTAL_BIG 1       // 1: ... and in the throughput variant
+#endif
 
 namespace gpuar {
 
@@ -129,7 +135,8 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     // initializeDecoder (:582-603): the first 16 bits
     uint32_t code = in.take(16u);
     refill();
-    uint32_t L = 0, V = 0;
+    constexpr bool kTotal = kRingFeed ? (GPUAR_DEC_TOTAL_SMALL != 0) : (GPUAR_DEC_TOTAL_BIG != 0);
+    uint32_t L = 0, V = kTotal ? 65536u : 0u;       // V = inverted upper bound, or the range itself (kTotal)
 
     const uint32_t max_raw = __reduce_max_sync(kFull, raw);
     uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)my * packet);
@@ -139,12 +146,20 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     auto step = [&](uint32_t i, uint32_t m, uint32_t sh, uint32_t slot) {
         const uint32_t T = 256u + i;
         uint32_t lo, cnt;
-        const uint32_t s = (kRingFeed || GPUAR_DEC_EARLY_BIG) ? tree_decode_early(root, tree, 32u, code, L, V, T, lo, cnt)
-                                     : tree_decode(root, tree, 32u, unscale(code, L, V, T), T, lo, cnt);
+        const uint32_t range = kTotal ? V : 65536u - V - L;
+        const uint32_t s = (kRingFeed || GPUAR_DEC_EARLY_BIG)
+                               ? tree_decode_early_range(root, tree, 32u, code, L, range, T, lo, cnt)
+                               : tree_decode(root, tree, 32u, unscale_range(code, L, range, T), T, lo, cnt);
         packed |= s << (8u * slot);
-        uint32_t k, u, U1;
-        narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
-        code = advance_code(code, k, u, in);
+        if (kTotal) {
+            uint32_t L1, Vx, t, As;
+            narrow_total(L, V, lo, lo + cnt, m, sh, L1, Vx, t, As);
+            code = advance_code_total(code, t, As, in);
+        } else {
+            uint32_t k, u, U1;
+            narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
+            code = advance_code(code, k, u, in);
+        }
         refill();
     };
 

@@ -145,9 +145,10 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
 }
 
 // ------------------------------------------------- scan + compaction, one pass
-// Tile = kTilePackets packets.  Decoupled look-back (Merrill & Garland) over the
-// per-tile byte totals: descriptor = flag(2 bits) | value(62 bits) in one 64-bit word.
-constexpr uint32_t kTilePackets = 64;
+// Tile = `tile` packets (the work unit of one CTA, 4..128, chosen by the launcher).  Decoupled
+// look-back (Merrill & Garland) over the per-tile byte totals: descriptor = flag(2 bits) |
+// value(62 bits) in one 64-bit word.
+constexpr uint32_t kMaxTilePackets = 128;
 constexpr uint32_t kCompactThreads = 256;
 
 // copy `len` bytes from src (16-byte aligned) to dst (any alignment) with one warp
@@ -163,10 +164,7 @@ __device__ __forceinline__ void warp_copy_unaligned(uint8_t *__restrict__ dst, c
     const uint32_t mis = (uint32_t)((uintptr_t)s & 15u);           // warp-uniform
     const uint4 *sa = reinterpret_cast<const uint4 *>(s - mis);
     const uint32_t wsh = mis >> 2, bsh = (mis & 3u) * 8u;
-    for (uint32_t c = lane; c < body; c += 32u) {
-        const uint4 v0 = sa[c];
-        uint4 v1 = make_uint4(0, 0, 0, 0);
-        if (mis) v1 = sa[c + 1];
+    auto realign = [&](const uint4 &v0, const uint4 &v1) {
         uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
         uint32_t q[5];
 #pragma unroll
@@ -178,7 +176,24 @@ __device__ __forceinline__ void warp_copy_unaligned(uint8_t *__restrict__ dst, c
         o.y = __funnelshift_r(q[1], q[2], bsh);
         o.z = __funnelshift_r(q[2], q[3], bsh);
         o.w = __funnelshift_r(q[3], q[4], bsh);
-        reinterpret_cast<uint4 *>(d)[c] = o;
+        return o;
+    };
+    // two 512-byte rows per iteration: all the loads of the iteration are in flight together
+    uint32_t c = lane;
+    for (; c + 32u < body; c += 64u) {
+        uint4 v0[2], v1[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            v0[r] = sa[c + 32u * r];
+            v1[r] = mis ? sa[c + 32u * r + 1u] : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) reinterpret_cast<uint4 *>(d)[c + 32u * r] = realign(v0[r], v1[r]);
+    }
+    for (; c < body; c += 32u) {
+        const uint4 v0 = sa[c];
+        const uint4 v1 = mis ? sa[c + 1] : make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4 *>(d)[c] = realign(v0, v1);
     }
     const uint32_t done = head + (body << 4);
     if (lane < len - done) dst[done + lane] = src[done + lane];
@@ -207,35 +222,42 @@ __device__ __forceinline__ void warp_copy_any(uint8_t *__restrict__ dst, const u
 
 __global__ void __launch_bounds__(kCompactThreads)
 compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const uint32_t *__restrict__ sizes,
-               uint32_t n_packets, uint8_t *__restrict__ payload, uint64_t *__restrict__ desc,
+               uint32_t n_packets, uint32_t tile_packets, uint8_t *__restrict__ payload, uint64_t *__restrict__ desc,
                uint32_t *__restrict__ ticket, uint64_t *__restrict__ total_out)
 {
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_off[kTilePackets + 1];
+    __shared__ uint32_t s_off[kMaxTilePackets + 1];
     __shared__ uint64_t s_base;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);          // tiles start in ticket order
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint32_t first = tile * kTilePackets;
-    const uint32_t count = min(kTilePackets, n_packets - first);
+    const uint32_t first = tile * tile_packets;
+    const uint32_t count = min(tile_packets, n_packets - first);
 
     if (warp == 0) {
-        // exclusive scan of this tile's 64 sizes (two per lane)
-        const uint32_t a = (2u * lane < count) ? sizes[first + 2u * lane] : 0u;
-        const uint32_t b = (2u * lane + 1u < count) ? sizes[first + 2u * lane + 1u] : 0u;
-        uint32_t inc = a + b;
+        // exclusive scan of this tile's sizes (four per lane)
+        uint32_t a[4], sum = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < 4u; ++i) {
+            a[i] = (4u * lane + i < count) ? sizes[first + 4u * lane + i] : 0u;
+            sum += a[i];
+        }
+        uint32_t inc = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(kFull, inc, d);
             if (lane >= (uint32_t)d) inc += t;
         }
-        const uint32_t ex = inc - (a + b);
-        s_off[2u * lane] = ex;
-        s_off[2u * lane + 1u] = ex + a;
+        uint32_t ex = inc - sum;
+#pragma unroll
+        for (uint32_t i = 0; i < 4u; ++i) {
+            s_off[4u * lane + i] = ex;
+            ex += a[i];
+        }
         const uint32_t total = __shfl_sync(kFull, inc, 31);
-        if (lane == 0) s_off[kTilePackets] = total;
+        if (lane == 0) s_off[kMaxTilePackets] = total;              // entry 4*lane+i == count already holds it when count < 128
 
         // decoupled look-back for the bytes that precede this tile
         const uint64_t base = lookback_exclusive(desc, tile, total, lane);
@@ -248,8 +270,8 @@ compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const ui
 
     const uint64_t base = s_base;
     for (uint32_t q = warp; q < count; q += kCompactThreads / 32u) {
-        const uint32_t len = s_off[q + 1u] - s_off[q];
-        warp_copy_unaligned(payload + base + s_off[q], slots + (size_t)(first + q) * slot_stride, len, lane);
+        warp_copy_unaligned(payload + base + s_off[q], slots + (size_t)(first + q) * slot_stride,
+                            s_off[q + 1u] - s_off[q], lane);
     }
 }
 
@@ -320,9 +342,29 @@ cudaError_t launch_encode_slots(const uint8_t *d_in, size_t n, uint8_t *d_slots,
     return cudaGetLastError();
 }
 
+// Work unit of the compaction.  0 = automatic: 64 packets (512 KiB of input) when that still
+// gives every SM several CTAs, fewer for small inputs (a 64 MiB input is 8192 packets: 128
+// CTAs of 64 packets would leave SMs idle and the copy latency-bound).
+static uint32_t g_compact_tile = 0;
+bool set_compact_tile(uint32_t packets_per_tile)
+{
+    if (packets_per_tile != 0 && (packets_per_tile < 4 || packets_per_tile > kMaxTilePackets ||
+                                  (packets_per_tile & (packets_per_tile - 1)) != 0))
+        return false;
+    g_compact_tile = packets_per_tile;
+    return true;
+}
+static uint32_t compact_tile_for(size_t packets)
+{
+    if (g_compact_tile) return g_compact_tile;
+    uint32_t tile = 64;
+    while (tile > 8 && packets / tile < 148u * 8u) tile >>= 1;
+    return tile;
+}
+
 size_t compact_desc_bytes(size_t packets)
 {
-    const size_t tiles = (packets + kTilePackets - 1) / kTilePackets;
+    const size_t tiles = (packets + 3) / 4;                         // the smallest tile there is
     return (tiles + 2) * sizeof(uint64_t);                          // descriptors + ticket word
 }
 
@@ -330,12 +372,13 @@ cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const u
                            uint32_t packets, uint8_t *d_payload, uint64_t *d_desc, uint64_t *d_total,
                            cudaStream_t st)
 {
-    const uint32_t tiles = (packets + kTilePackets - 1) / kTilePackets;
-    cudaError_t e = cudaMemsetAsync(d_desc, 0, compact_desc_bytes(packets), st);
+    const uint32_t tile = compact_tile_for(packets);
+    const uint32_t tiles = (packets + tile - 1) / tile;
+    cudaError_t e = cudaMemsetAsync(d_desc, 0, ((size_t)tiles + 2) * sizeof(uint64_t), st);
     if (e != cudaSuccess) return e;
     if (!packets) return cudaMemsetAsync(d_total, 0, sizeof(uint64_t), st);
     uint32_t *ticket = reinterpret_cast<uint32_t *>(d_desc + tiles);
-    compact_kernel<<<tiles, kCompactThreads, 0, st>>>(d_slots, slot_stride, d_sizes, packets, d_payload,
+    compact_kernel<<<tiles, kCompactThreads, 0, st>>>(d_slots, slot_stride, d_sizes, packets, tile, d_payload,
                                                       d_desc, ticket, d_total);
     count_launch();
     return cudaGetLastError();

@@ -2,70 +2,74 @@
 // the machine (a 64 MiB input is 8192 packets = 256 lane=packet warps for 592 warp schedulers).
 //
 // Same arithmetic as encode_kernel (coder_math.h), same output, but the stages of a symbol
-// step run in four different warps of a 128-thread CTA that owns 32 packets:
-//     warp 0  MODEL-A  tree levels 0-1              -> ring A (partial cum[s])
-//     warp 1  MODEL-B  tree levels 2-3              -> ring B (partial cum[s] | count[s] << 16)
-//     warp 2  CODER    narrow_renorm (the chain)    -> ring F (k | u << 5 | U1 << 9)
-//     warp 3  BITS     emit_field / bit sink        -> the packet's slot
-// (the tree levels are independent of each other given the symbol, so the model splits in
-// two).  Each warp keeps lane = packet, so per-packet state never crosses lanes; the rings
-// are double buffered per round of 32 positions and handed over with named barriers
-// (bar.arrive on the producer side, bar.sync on the consumer side).  Only CODER carries the
-// serial dependence of arithmetic coding.
+// step run in six different warps of a 192-thread CTA that owns 32 packets:
+//     warp 0  MODEL-A  tree levels 0-1               -> ring A (partial cum[s])
+//     warp 1  MODEL-B  tree level 2                  -> ring B (partial cum[s])
+//     warp 2  MODEL-D  tree level 3 (the leaves)     -> ring D (partial cum[s] | count[s] << 16)
+//     warp 3  FIELD    k, u and the bit field        -> ring F (pack_field descriptor)
+//     warp 4  BITS     bit sink                      -> the packet's slot
+//     warp 5  CODER    narrow_lazy (the chain)       -> ring C (L1 | U1 << 16)
+// The tree levels are independent of each other given the symbol, so the model splits by
+// level.  Only CODER carries the serial dependence of arithmetic coding, and it carries the
+// minimum: the interval recurrence with its single normalisation (narrow_lazy); how the
+// total shift splits into matching-MSB and underflow shifts -- two count-leading-zeros --
+// is worked out by FIELD, which has no state at all, and everything of the emission that
+// depends on the pending-underflow counter by BITS.  CODER is the highest warp of the CTA
+// because the SM sub-partition arbiter favours the highest warp slot.
+// Each warp keeps lane = packet, so per-packet state never crosses lanes; the rings are
+// double buffered per round of 32 positions and handed over with named barriers
+// (bar.arrive on the producer side, bar.sync on the consumer side).  The three model rings
+// share one full/empty barrier pair per buffer (128 threads: three producers + CODER).
 #include "common.cuh"
 #include "kernels.h"
 
-#ifndef GPUAR_WS_CODER_UNROLL
-#define GPUAR_WS_CODER_UNROLL 8     // tuning knob: steps per unrolled block of the CODER warp
+#ifndef GPUAR_WS_CODER_BLOCK
+#define GPUAR_WS_CODER_BLOCK 4      // tuning knob: steps per straight-line block of the CODER warp
 #endif
 
 namespace gpuar {
 
 constexpr uint32_t kRound = 32;
-constexpr int kCoderUnroll = GPUAR_WS_CODER_UNROLL;
+constexpr uint32_t kCoderBlock = GPUAR_WS_CODER_BLOCK;
+constexpr uint32_t kWsThreads = 192;
+#ifndef GPUAR_WS_SWAP_BD
+#define GPUAR_WS_SWAP_BD 0          // tuning knob: which of warps 1 / 2 takes level 2 and which the leaves
+#endif
+constexpr uint32_t kRoleB = GPUAR_WS_SWAP_BD ? 2u : 1u, kRoleD = GPUAR_WS_SWAP_BD ? 1u : 2u;
 
 struct WsShared {
-    uint64_t tree[kTreeStored][32];      // 21504 B: nodes 0-3 MODEL-A, nodes 4-83 MODEL-B
-    uint32_t ring_a[2][kRound][32];      //  8192 B, MODEL-A -> CODER
-    uint32_t ring_b[2][kRound][32];      //  8192 B, MODEL-B -> CODER
-    uint32_t ring_f[2][kRound][32];      //  8192 B, CODER   -> BITS
+    uint64_t tree[kTreeStored][32];      // 21504 B: nodes 0-3 MODEL-A, 4-19 MODEL-B, 20-83 MODEL-D
+    uint32_t ring_a[2][kRound][32];      //  8192 B each (MODEL -> CODER)
+    uint32_t ring_b[2][kRound][32];
+    uint32_t ring_d[2][kRound][32];
+    uint32_t ring_c[2][kRound][32];      // CODER -> FIELD
+    uint2 ring_f[2][kRound][32];         // FIELD -> BITS (16384 B: two-word descriptors)
+    uint32_t stage[3][8][32];            // the model warps' input words of the current round
     uint32_t final_l[32];                // CODER -> BITS at the end of the packet
 };
 
-// named barriers (0 is __syncthreads); each is shared by exactly two warps = 64 threads
-enum : uint32_t { kAFull = 1, kAEmpty = 3, kBFull = 5, kBEmpty = 7, kFFull = 9, kFEmpty = 11, kDone = 13 };
+// named barriers (0 is __syncthreads); id + buffer index
+enum : uint32_t { kInFull = 1, kInEmpty = 3, kCFull = 5, kCEmpty = 7, kFFull = 9, kFEmpty = 11, kDone = 13 };
+constexpr uint32_t kInCount = 128;       // MODEL-A, MODEL-B, MODEL-D, CODER
+constexpr uint32_t kPairCount = 64;      // one producer warp + one consumer warp
 
-__device__ __forceinline__ void bar_sync(uint32_t id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+template <uint32_t kCount>
+__device__ __forceinline__ void bar_sync(uint32_t id)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kCount) : "memory");
+}
+template <uint32_t kCount>
 __device__ __forceinline__ void bar_arrive(uint32_t id)
 {
     __threadfence_block();                                       // ring writes visible before the hand-over
-    asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kCount) : "memory");
 }
 
-// the packet's input, 16 bytes per lane per half round, fetched one half round ahead
-struct SymbolFeed {
-    const uint4 *in16;
-    uint32_t len;
-    uint4 buf_a, buf_b;
-    __device__ __forceinline__ uint4 fetch(uint32_t g) const
-    {
-        return (g * 16u < len) ? __ldg(in16 + g) : make_uint4(0, 0, 0, 0);
-    }
-    __device__ __forceinline__ void start(const uint8_t *p, uint32_t n)
-    {
-        in16 = reinterpret_cast<const uint4 *>(p);
-        len = n;
-        buf_a = fetch(0);
-        buf_b = fetch(1);
-    }
-};
-
-__device__ __forceinline__ uint32_t word_of(const uint4 &c, uint32_t q)
-{
-    return q == 0u ? c.x : q == 1u ? c.y : q == 2u ? c.z : c.w;
-}
-
-// MODEL-A (kRole 0: root + level 1, ring A) or MODEL-B (kRole 1: level 2 + leaves, ring B)
+// kRole 0: root + level 1 -> ring A;  1: level 2 -> ring B;  2: leaves -> ring D.
+// The packet's input arrives as two 16-byte loads per lane and round, issued one round ahead;
+// at the top of a round the eight words go to the warp's staging area (stage[word][lane]: the
+// lane's own column, so no synchronisation) and the symbol loop picks them up by index --
+// selecting among eight registers with a run-time index would cost more than the model step.
 template <int kRole>
 __device__ __forceinline__ void model_warp(WsShared &sm, uint64_t *tree, const uint8_t *in, uint32_t len,
                                            uint32_t min_len, uint32_t rounds, uint32_t lane)
@@ -73,52 +77,59 @@ __device__ __forceinline__ void model_warp(WsShared &sm, uint64_t *tree, const u
     uint64_t root = tree_node_init(64);                          // MODEL-A only
     if (kRole == 0) {
         for (uint32_t nd = 0; nd < 4u; ++nd) tree[nd * 32u] = tree_node_init(16);
-    } else {
+    } else if (kRole == 1) {
         for (uint32_t nd = 4u; nd < 20u; ++nd) tree[nd * 32u] = tree_node_init(4);
+    } else {
         for (uint32_t nd = 20u; nd < kTreeStored; ++nd) tree[nd * 32u] = enc_leaf_init();
     }
-    uint32_t(*ring)[kRound][32] = kRole == 0 ? sm.ring_a : sm.ring_b;
-    constexpr uint32_t full_id = kRole == 0 ? kAFull : kBFull, empty_id = kRole == 0 ? kAEmpty : kBEmpty;
-    auto model = [&](uint32_t s) -> uint32_t {
-        if (kRole == 0) return tree_encode_upper(root, tree, 32u, s);
-        uint32_t cnt;
-        const uint32_t lo = tree_encode_lower(tree, 32u, s, cnt);
-        return lo | (cnt << 16);
+    uint32_t(*ring)[kRound][32] = kRole == 0 ? sm.ring_a : kRole == 1 ? sm.ring_b : sm.ring_d;
+    uint32_t(*stage)[32] = sm.stage[kRole];
+    auto fields = [&](uint32_t word) -> WordFields {
+        return kRole == 0 ? word_fields_upper(word) : kRole == 1 ? word_fields_mid(word) : word_fields_leaf(word);
     };
-    SymbolFeed feed;
-    feed.start(in, len);
+    auto model = [&](WordFields f, uint32_t j) -> uint32_t {    // symbol j of the word the fields come from
+        if (kRole == 0) return tree_encode_upper_word(root, tree, 32u, f, j);
+        if (kRole == 1) return tree_encode_mid_word(tree, 32u, f, j);
+        uint32_t cnt;
+        const uint32_t lo = tree_encode_leaf_word(tree, 32u, f, j, cnt);
+        return cnt * 65536u + lo;                                // fields cannot overlap: a multiply-add, not shift + or
+    };
+    const uint4 *const in16 = reinterpret_cast<const uint4 *>(in);
+    auto fetch = [&](uint32_t g) -> uint4 {
+        return (g * 16u < len) ? __ldg(in16 + g) : make_uint4(0, 0, 0, 0);
+    };
+    uint4 buf_a = fetch(0), buf_b = fetch(1);
     for (uint32_t r = 0; r < rounds; ++r) {
         const uint32_t b = r & 1u, i0 = r * kRound;
-        if (r >= 2u) bar_sync(empty_id + b);
-        const bool full = i0 + kRound <= min_len;
-        auto half = [&](const uint4 &c, uint32_t h) {
+        stage[0][lane] = buf_a.x, stage[1][lane] = buf_a.y, stage[2][lane] = buf_a.z, stage[3][lane] = buf_a.w;
+        stage[4][lane] = buf_b.x, stage[5][lane] = buf_b.y, stage[6][lane] = buf_b.z, stage[7][lane] = buf_b.w;
+        buf_a = fetch(2u * r + 2u);
+        buf_b = fetch(2u * r + 3u);
+        if (r >= 2u) bar_sync<kInCount>(kInEmpty + b);
+        if (i0 + kRound <= min_len) {
 #pragma unroll 1
-            for (uint32_t q = 0; q < 4u; ++q) {
-                const uint32_t word = word_of(c, q);
-                const uint32_t j0 = 16u * h + 4u * q;
-                if (full) {
+            for (uint32_t w = 0; w < 8u; ++w) {
+                const WordFields f = fields(stage[w][lane]);
 #pragma unroll
-                    for (uint32_t j = 0; j < 4u; ++j) ring[b][j0 + j][lane] = model((word >> (8u * j)) & 0xFFu);
-                } else {
-#pragma unroll 1
-                    for (uint32_t j = 0; j < 4u; ++j)
-                        ring[b][j0 + j][lane] = (i0 + j0 + j < len) ? model((word >> (8u * j)) & 0xFFu) : 0u;
-                }
+                for (uint32_t j = 0; j < 4u; ++j) ring[b][4u * w + j][lane] = model(f, j);
             }
-        };
-        half(feed.buf_a, 0u);
-        feed.buf_a = feed.fetch(2u * r + 2u);
-        half(feed.buf_b, 1u);
-        feed.buf_b = feed.fetch(2u * r + 3u);
-        bar_arrive(full_id + b);
+        } else {
+#pragma unroll 1
+            for (uint32_t j = 0; j < kRound; ++j) {
+                const WordFields f = fields(stage[j >> 2][lane]);
+                ring[b][j][lane] = (i0 + j < len) ? model(f, j & 3u) : 0u;
+            }
+        }
+        bar_arrive<kInCount>(kInFull + b);
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kWsThreads)
 encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ slots, uint32_t slot_stride,
                  uint32_t *__restrict__ sizes, uint32_t n_packets, uint32_t packet)
 {
-    __shared__ __align__(16) WsShared sm;
+    extern __shared__ __align__(16) uint8_t ws_smem[];           // 62.6 KB: above the static limit
+    WsShared &sm = *reinterpret_cast<WsShared *>(ws_smem);
     const uint32_t lane = lane_id();
     const uint32_t role = threadIdx.x >> 5;
     const uint32_t my = blockIdx.x * 32u + lane;
@@ -126,60 +137,104 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
     const size_t off = (size_t)my * packet;
     uint32_t len = 0;
     if (mine) len = (n - off < packet) ? (uint32_t)(n - off) : packet;
-    const uint32_t max_len = __reduce_max_sync(kFull, len);      // identical in the four warps
+    const uint32_t max_len = __reduce_max_sync(kFull, len);      // identical in all the warps
     const uint32_t min_len = __reduce_min_sync(kFull, mine ? len : packet);
     const uint32_t rounds = (max_len + kRound - 1u) / kRound;
     uint64_t *const tree = &sm.tree[0][lane];
 
     if (role == 0u) {
         model_warp<0>(sm, tree, src + off, len, min_len, rounds, lane);
-    } else if (role == 1u) {
+    } else if (role == kRoleB) {
         model_warp<1>(sm, tree, src + off, len, min_len, rounds, lane);
-    } else if (role == 2u) {
+    } else if (role == kRoleD) {
+        model_warp<2>(sm, tree, src + off, len, min_len, rounds, lane);
+    } else if (role == 5u) {
         // ------------------------------------------------------------ CODER
-        uint32_t L = 0, V = 0;
+        uint32_t L = 0, R1 = 65536u, sx = 0;                      // narrow_lazy state: range = R1 >> sx
         for (uint32_t r = 0; r < rounds; ++r) {
             const uint32_t b = r & 1u, i0 = r * kRound;
             uint32_t sh;
             const uint32_t m_l = magic_for(256u + i0 + lane, sh);
             sh = shift_for(256u + i0);
             const bool full = i0 + kRound <= min_len;
-            bar_sync(kAFull + b);
-            bar_sync(kBFull + b);
-            if (r >= 2u) bar_sync(kFEmpty + b);
+            bar_sync<kInCount>(kInFull + b);
+            if (r >= 2u) bar_sync<kPairCount>(kCEmpty + b);
             if (full) {
-#pragma unroll kCoderUnroll
-                for (uint32_t j = 0; j < kRound; ++j) {
-                    const uint32_t m = __shfl_sync(kFull, m_l, j);
-                    const uint32_t pa = sm.ring_a[b][j][lane], pb = sm.ring_b[b][j][lane];
-                    uint32_t k, u, U1;
-                    const uint32_t lo = pa + (pb & 0xFFFFu);
-                    narrow_renorm(L, V, lo, lo + (pb >> 16), m, sh, k, u, U1);
-                    sm.ring_f[b][j][lane] = k | (u << 5) | (U1 << 9) | 0x80000000u;
+                // blocks of kCoderBlock steps: everything that does not depend on the coder state
+                // (ring loads, the sums of the partial counts, the multipliers) is gathered for the
+                // whole block first, so that the chain finds its operands in registers
+#pragma unroll 1
+                for (uint32_t j0 = 0; j0 < kRound; j0 += kCoderBlock) {
+                    uint32_t lo[kCoderBlock], hi[kCoderBlock], m[kCoderBlock];
+#pragma unroll
+                    for (uint32_t j = 0; j < kCoderBlock; ++j) {
+                        const uint32_t pd = sm.ring_d[b][j0 + j][lane];
+                        lo[j] = sm.ring_a[b][j0 + j][lane] + sm.ring_b[b][j0 + j][lane] + (pd & 0xFFFFu);
+                        hi[j] = lo[j] + (pd >> 16);
+                        m[j] = __shfl_sync(kFull, m_l, j0 + j);
+                    }
+#pragma unroll
+                    for (uint32_t j = 0; j < kCoderBlock; ++j) {
+                        uint32_t L1, Vx;
+                        narrow_lazy(L, R1, sx, lo[j], hi[j], m[j], sh, L1, Vx);
+                        sm.ring_c[b][j0 + j][lane] = pack_bounds(L1, Vx);
+                    }
                 }
             } else {
 #pragma unroll 1
                 for (uint32_t j = 0; j < kRound; ++j) {
                     const uint32_t m = __shfl_sync(kFull, m_l, j);
-                    const uint32_t pa = sm.ring_a[b][j][lane], pb = sm.ring_b[b][j][lane];
-                    uint32_t f = 0;
+                    const uint32_t pd = sm.ring_d[b][j][lane];
+                    const uint32_t lo = sm.ring_a[b][j][lane] + sm.ring_b[b][j][lane] + (pd & 0xFFFFu);
+                    uint32_t c = 0;
                     if (i0 + j < len) {
-                        uint32_t k, u, U1;
-                        const uint32_t lo = pa + (pb & 0xFFFFu);
-                        narrow_renorm(L, V, lo, lo + (pb >> 16), m, sh, k, u, U1);
-                        f = k | (u << 5) | (U1 << 9) | 0x80000000u;
+                        uint32_t L1, Vx;
+                        narrow_lazy(L, R1, sx, lo, lo + (pd >> 16), m, sh, L1, Vx);
+                        c = pack_bounds(L1, Vx);
                     }
-                    sm.ring_f[b][j][lane] = f;
+                    sm.ring_c[b][j][lane] = c;
                 }
             }
-            if (r + 2u < rounds) {
-                bar_arrive(kAEmpty + b);
-                bar_arrive(kBEmpty + b);
-            }
-            bar_arrive(kFFull + b);
+            if (r + 2u < rounds) bar_arrive<kInCount>(kInEmpty + b);
+            bar_arrive<kPairCount>(kCFull + b);
         }
         sm.final_l[lane] = L;
-        bar_arrive(kDone);
+        bar_arrive<kPairCount>(kDone);
+    } else if (role == 3u) {
+        // ------------------------------------------------------------ FIELD (stateless)
+        for (uint32_t r = 0; r < rounds; ++r) {
+            const uint32_t b = r & 1u, i0 = r * kRound;
+            const bool full = i0 + kRound <= min_len;
+            bar_sync<kPairCount>(kCFull + b);
+            if (r >= 2u) bar_sync<kPairCount>(kFEmpty + b);
+            if (full) {
+                // straight-line blocks of eight independent steps: the count-leading-zeros latencies overlap
+#pragma unroll 1
+                for (uint32_t j0 = 0; j0 < kRound; j0 += 8u) {
+                    uint32_t c[8];
+#pragma unroll
+                    for (uint32_t j = 0; j < 8u; ++j) c[j] = sm.ring_c[b][j0 + j][lane];
+#pragma unroll
+                    for (uint32_t j = 0; j < 8u; ++j) {
+                        uint32_t k, u;
+                        shifts_of(c[j] & 0xFFFFu, c[j] >> 16, k, u);
+                        const FieldDesc d = pack_field(k, u, c[j]);
+                        sm.ring_f[b][j0 + j][lane] = make_uint2(d.w0, d.w1);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t j = 0; j < kRound; ++j) {
+                    const uint32_t c = sm.ring_c[b][j][lane];
+                    uint32_t k, u;
+                    shifts_of(c & 0xFFFFu, c >> 16, k, u);
+                    const FieldDesc d = pack_field(k, u, c);
+                    sm.ring_f[b][j][lane] = (i0 + j < len) ? make_uint2(d.w0, d.w1) : make_uint2(0u, 0u);
+                }
+            }
+            if (r + 2u < rounds) bar_arrive<kPairCount>(kCEmpty + b);
+            bar_arrive<kPairCount>(kFFull + b);
+        }
     } else {
         // ------------------------------------------------------------ BITS
         uint32_t pend = 0;
@@ -193,39 +248,42 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
         for (uint32_t r = 0; r < rounds; ++r) {
             const uint32_t b = r & 1u, i0 = r * kRound;
             const bool full = i0 + kRound <= min_len;
-            bar_sync(kFFull + b);
+            bar_sync<kPairCount>(kFFull + b);
             if (full) {
                 // four steps per block.  The rare long-underflow path needs pend > 16 at a step
                 // with k != 0; pend grows by at most the u's of the group, so one warp-uniform
                 // vote on (pend + sum of u) covers the whole group and the common block has no
-                // branch at all: its four ring loads issue together.
+                // branch at all: its four ring loads issue together.  The rare block reads the
+                // ring again rather than indexing the four registers (which would put them on
+                // the stack for the common block too).
 #pragma unroll 1
                 for (uint32_t j0 = 0; j0 < kRound; j0 += 4u) {
-                    uint32_t f[4];
-#pragma unroll
-                    for (uint32_t j = 0; j < 4u; ++j) f[j] = sm.ring_f[b][j0 + j][lane];
-                    const uint32_t usum = ((f[0] >> 5) & 15u) + ((f[1] >> 5) & 15u) + ((f[2] >> 5) & 15u) +
-                                          ((f[3] >> 5) & 15u);
+                    const uint2 f0 = sm.ring_f[b][j0][lane], f1 = sm.ring_f[b][j0 + 1u][lane],
+                                f2 = sm.ring_f[b][j0 + 2u][lane], f3 = sm.ring_f[b][j0 + 3u][lane];
+                    const uint32_t usum = (f0.x >> 28) + (f1.x >> 28) + (f2.x >> 28) + (f3.x >> 28);
                     if (__any_sync(kFull, pend + usum > 16u)) {
 #pragma unroll 1
-                        for (uint32_t j = 0; j < 4u; ++j)         // rare path: small code; f[] spills to 16 B of stack here only
-                            emit_symbol(out, pend, f[j] & 31u, (f[j] >> 5) & 15u, (f[j] >> 9) & 0xFFFFu);
+                        for (uint32_t j = 0; j < 4u; ++j) {
+                            const uint2 f = sm.ring_f[b][j0 + j][lane];
+                            emit_packed_any(out, pend, FieldDesc{f.x, f.y});
+                        }
                     } else {
-#pragma unroll
-                        for (uint32_t j = 0; j < 4u; ++j)
-                            emit_field(out, pend, f[j] & 31u, (f[j] >> 5) & 15u, (f[j] >> 9) & 0xFFFFu);
+                        emit_packed(out, pend, FieldDesc{f0.x, f0.y});
+                        emit_packed(out, pend, FieldDesc{f1.x, f1.y});
+                        emit_packed(out, pend, FieldDesc{f2.x, f2.y});
+                        emit_packed(out, pend, FieldDesc{f3.x, f3.y});
                     }
                 }
             } else {
 #pragma unroll 1
                 for (uint32_t j = 0; j < kRound; ++j) {
-                    const uint32_t f = sm.ring_f[b][j][lane];
-                    if (f >> 31) emit_symbol(out, pend, f & 31u, (f >> 5) & 15u, (f >> 9) & 0xFFFFu);
+                    const uint2 f = sm.ring_f[b][j][lane];
+                    if (field_valid(FieldDesc{f.x, f.y})) emit_packed_any(out, pend, FieldDesc{f.x, f.y});
                 }
             }
-            if (r + 2u < rounds) bar_arrive(kFEmpty + b);
+            if (r + 2u < rounds) bar_arrive<kPairCount>(kFEmpty + b);
         }
-        bar_sync(kDone);
+        bar_sync<kPairCount>(kDone);
         if (mine) {
             const uint32_t comp = finish_packet(out, sm.final_l[lane], pend, slot, len);
             if (sizes) sizes[my] = comp;
@@ -238,7 +296,12 @@ cudaError_t launch_encode_slots_ws(const uint8_t *d_in, size_t n, uint8_t *d_slo
 {
     const uint32_t packets = (uint32_t)((n + packet - 1) / packet);
     if (!packets) return cudaSuccess;
-    encode_ws_kernel<<<(packets + 31u) / 32u, 128, 0, st>>>(d_in, n, d_slots, slot_stride, d_sizes, packets, packet);
+    // per device: the attribute belongs to the function of the current context
+    cudaError_t e = cudaFuncSetAttribute(encode_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(WsShared));
+    if (e != cudaSuccess) return e;
+    encode_ws_kernel<<<(packets + 31u) / 32u, kWsThreads, sizeof(WsShared), st>>>(d_in, n, d_slots, slot_stride,
+                                                                                   d_sizes, packets, packet);
     count_launch();
     return cudaGetLastError();
 }

@@ -12,10 +12,11 @@ const void *probe_kernel();   // address of a kernel of this library, for image-
 // 16112 is coded correctly (the reference's own limit, compressor.cpp:13)
 cudaError_t launch_encode_slots(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t slot_stride,
                                 uint32_t *d_sizes, uint32_t packet, cudaStream_t st);
-// encode_ws.cu: same contract, three warps per 32 packets (for inputs that cannot fill the GPU)
+// encode_ws.cu: same contract, six specialised warps per 32 packets (for inputs that cannot fill the GPU)
 cudaError_t launch_encode_slots_ws(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t slot_stride,
                                    uint32_t *d_sizes, uint32_t packet, cudaStream_t st);
 size_t compact_desc_bytes(size_t packets);
+bool set_compact_tile(uint32_t packets_per_tile);   // 0 = automatic, else a power of two 4..128
 cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const uint32_t *d_sizes,
                            uint32_t packets, uint8_t *d_payload, uint64_t *d_desc, uint64_t *d_total,
                            cudaStream_t st);

@@ -180,6 +180,8 @@ void garDecompressExecutor(const uint8_t *source, size_t size, uint8_t *destinat
  * inputs).  Default: chosen by packet count. */
 #define GPUAR_OPT_ENCODE_PATH 1      /* 0 auto (default), 1 fused, 2 warp-specialised */
 #define GPUAR_OPT_WS_MAX_PACKETS 2   /* auto: use the warp-specialised kernel up to this many packets */
+#define GPUAR_OPT_COMPACT_TILE 3     /* packets per work unit of the scan + compaction kernel: 0 auto (default),
+                                        or a power of two 4..128 (32 KiB .. 1 MiB of input per CTA) */
 int gpuar_b200_set_option(int key, long long value);
 
 /* ----------------------------------------------------------- measurement hooks

@@ -38,6 +38,60 @@ uint32_t host_model_encode_packet(const uint8_t *x, uint32_t n, uint8_t *slot, u
     return finish_packet(out, L, pend, slot, n);
 }
 
+// the same packet through the stages of encode_ws_kernel: three model warps (levels 0-1, 2, 3),
+// CODER on the single-normalisation step, FIELD (k, u, packed descriptor), BITS
+uint32_t host_model_encode_packet_ws(const uint8_t *x, uint32_t n, uint8_t *slot, uint32_t slot_bytes)
+{
+    std::vector<uint64_t> tree(kTreeStored);
+    uint64_t root;
+    enc_tree_init(root, tree.data(), 1);
+    uint32_t L = 0, R = 65536, sx = 0, pend = 0;
+    BitSink out;
+    out.acc = 0;
+    out.nb = 0;
+    out.widx = 0;
+    out.wcap = (slot_bytes - kHdr) >> 2;
+    out.words = reinterpret_cast<uint32_t *>(slot + kHdr);
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t sh;
+        const uint32_t m = magic_for(256u + i, sh);
+        uint32_t cnt, L1, Vx, k, u;
+        // the model warps take their symbols four at a time from one input word
+        uint32_t word = 0;
+        memcpy(&word, x + (i & ~3u), (n - (i & ~3u)) < 4u ? (n - (i & ~3u)) : 4u);
+        const uint32_t pa = tree_encode_upper_word(root, tree.data(), 1, word_fields_upper(word), i & 3u);
+        const uint32_t pb = tree_encode_mid_word(tree.data(), 1, word_fields_mid(word), i & 3u);
+        const uint32_t lo_d = tree_encode_leaf_word(tree.data(), 1, word_fields_leaf(word), i & 3u, cnt);
+        const uint32_t pd = cnt * 65536u + lo_d;
+        const uint32_t lo = pa + pb + (pd & 0xFFFFu);
+        narrow_lazy(L, R, sx, lo, lo + (pd >> 16), m, sh, L1, Vx);
+        const uint32_t c = pack_bounds(L1, Vx);                    // ring C entry
+        const uint32_t U1 = c >> 16;
+        shifts_of(c & 0xFFFFu, U1, k, u);
+        emit_packed_any(out, pend, pack_field(k, u, c));
+    }
+    return finish_packet(out, L, pend, slot, n);
+}
+
+static size_t encode_stream_with(uint32_t (*enc)(const uint8_t *, uint32_t, uint8_t *, uint32_t), const uint8_t *in,
+                                 size_t n, uint8_t *payload, uint32_t packet)
+{
+    std::vector<uint8_t> slot(packet + 512 + 16);
+    size_t pos = 0;
+    for (size_t off = 0; off < n; off += packet) {
+        const uint32_t m = (uint32_t)(n - off < packet ? n - off : packet);
+        const uint32_t len = enc(in + off, m, slot.data(), packet + 512);
+        memcpy(payload + pos, slot.data(), len);
+        pos += len;
+    }
+    return pos;
+}
+
+size_t host_model_encode_stream_ws(const uint8_t *in, size_t n, uint8_t *payload, uint32_t packet)
+{
+    return encode_stream_with(host_model_encode_packet_ws, in, n, payload, packet);
+}
+
 size_t host_model_encode_stream(const uint8_t *in, size_t n, uint8_t *payload, uint32_t packet)
 {
     std::vector<uint8_t> slot(packet + 512 + 16);
@@ -53,7 +107,8 @@ size_t host_model_encode_stream(const uint8_t *in, size_t n, uint8_t *payload, u
 
 // decode the packet at byte offset `off` of a padded, 4-byte aligned payload exactly as a
 // lane of decode_kernel does; returns bytes produced
-static uint32_t decode_packet(const uint8_t *payload, size_t readable, size_t off, uint8_t *out, bool early)
+static uint32_t decode_packet(const uint8_t *payload, size_t readable, size_t off, uint8_t *out, bool early,
+                              bool total = false)
 {
     std::vector<uint64_t> tree(kTreeStored);
     uint64_t root;
@@ -80,12 +135,20 @@ static uint32_t decode_packet(const uint8_t *payload, size_t readable, size_t of
         uint32_t sh;
         const uint32_t m = magic_for(T, sh);
         uint32_t lo, cnt;
-        const uint32_t s = early ? tree_decode_early(root, tree.data(), 1, code, L, V, T, lo, cnt)
-                                 : tree_decode(root, tree.data(), 1, unscale(code, L, V, T), T, lo, cnt);
+        if (total && i == 0) V = 65536u;                           // V holds the range in this variant
+        const uint32_t range = total ? V : 65536u - V - L;
+        const uint32_t s = early ? tree_decode_early_range(root, tree.data(), 1, code, L, range, T, lo, cnt)
+                                 : tree_decode(root, tree.data(), 1, unscale_range(code, L, range, T), T, lo, cnt);
         out[i] = (uint8_t)s;
-        uint32_t k, u, U1;
-        narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
-        code = advance_code(code, k, u, in);
+        if (total) {
+            uint32_t L1, Vx, t, As;
+            narrow_total(L, V, lo, lo + cnt, m, sh, L1, Vx, t, As);
+            code = advance_code_total(code, t, As, in);
+        } else {
+            uint32_t k, u, U1;
+            narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
+            code = advance_code(code, k, u, in);
+        }
         if (in.hungry()) { in.feed(ahead); ++wp; ahead = word(wp); }
     }
     return raw;
@@ -100,6 +163,12 @@ uint32_t host_model_decode_packet(const uint8_t *payload, size_t readable, size_
 uint32_t host_model_decode_packet_early(const uint8_t *payload, size_t readable, size_t off, uint8_t *out)
 {
     return decode_packet(payload, readable, off, out, true);
+}
+
+// both with the single-normalisation step (decode_kernel with GPUAR_DEC_TOTAL_*)
+uint32_t host_model_decode_packet_total(const uint8_t *payload, size_t readable, size_t off, uint8_t *out, int early)
+{
+    return decode_packet(payload, readable, off, out, early != 0, true);
 }
 
 // exhaustive-ish check of the reciprocal division: for every total T and for numerators
@@ -155,6 +224,20 @@ uint64_t host_model_check_renorm(uint64_t seed, uint32_t count, uint32_t packet)
         const uint32_t m = magic_for(T, sh);
         narrow_renorm(L, V, cl, ch, m, sh, k, u, U1);
         bad += (L != Lr) || ((V ^ 0xFFFFu) != U) || (k != kk) || (u != uu) || (U1 != U1ref);
+        // the single-normalisation form of the same step (narrow_total + shifts_of)
+        uint32_t L2 = lo16, R2 = hi16 - lo16 + 1u, L1, Vx, t, As, k2, u2;
+        narrow_total(L2, R2, cl, ch, m, sh, L1, Vx, t, As);
+        const uint32_t U1b = (~Vx) & 0xFFFFu;
+        shifts_of(L1, U1b, k2, u2);
+        bad += (L2 != Lr) || (R2 != (uint32_t)U - Lr + 1u) || (U1b != U1ref) || (k2 != kk) || (u2 != uu);
+        bad += (t != kk + uu) || (((As >> 15) & 1u) != (uu ? 1u : 0u));
+        // and the lazy form, entered with the range held as is (sx = 0) or doubled (sx = 1)
+        for (uint32_t pre = 0; pre < 2u; ++pre) {
+            uint32_t L3 = lo16, R3 = (hi16 - lo16 + 1u) << pre, s3 = pre, L1c, Vxc;
+            narrow_lazy(L3, R3, s3, cl, ch, m, sh, L1c, Vxc);
+            bad += (L3 != Lr) || ((R3 >> s3) != (uint32_t)U - Lr + 1u) || (L1c != L1) || (Vxc != Vx) ||
+                   (s3 && (R3 & 1u)) || R3 <= 32768u || R3 > 65536u;
+        }
     }
     return bad;
 }

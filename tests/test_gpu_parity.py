@@ -116,6 +116,22 @@ def test_packet_size_sweep_equals_rebuilt_reference(dev, packet, path):
     assert np.array_equal(back, data)
 
 
+@pytest.mark.parametrize("tile", [4, 8, 16, 32, 64, 128])
+def test_compaction_work_unit_sweep(dev, tile):
+    """BASELINE config 5, second half: 8192-byte packets, work unit of the scan + compaction kernel swept
+    from 32 KiB to 1 MiB of input per CTA.  The stream must not depend on it."""
+    from gpuar_b200 import _lib
+    _lib.set_option(_lib.OPT_COMPACT_TILE, tile)
+    try:
+        for n in (1, 8192 * 3 + 7, 8192 * tile, 8192 * tile + 1, 8192 * (3 * tile + 1) + 100, 8192 * 700 + 33):
+            data = D.mixed(n + tile, n)
+            assert np.array_equal(dev_encode(dev, data), O.encode(data)), (tile, n)
+        data = make_input(VECTORS["m1m"])
+        assert md5(dev_encode(dev, data)) == VECTORS["m1m"]["payload_md5"]
+    finally:
+        _lib.set_option(_lib.OPT_COMPACT_TILE, 0)
+
+
 # ------------------------------------------------------------------ index
 @pytest.mark.parametrize("name", SMALL)
 def test_index_equals_chain_walk(dev, name):

@@ -26,10 +26,14 @@ def model():
     lib = C.CDLL(SO)
     lib.host_model_encode_stream.restype = C.c_size_t
     lib.host_model_encode_stream.argtypes = [O._u8p, C.c_size_t, O._u8p, C.c_uint32]
+    lib.host_model_encode_stream_ws.restype = C.c_size_t
+    lib.host_model_encode_stream_ws.argtypes = [O._u8p, C.c_size_t, O._u8p, C.c_uint32]
     lib.host_model_decode_packet.restype = C.c_uint32
     lib.host_model_decode_packet.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p]
     lib.host_model_decode_packet_early.restype = C.c_uint32
     lib.host_model_decode_packet_early.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p]
+    lib.host_model_decode_packet_total.restype = C.c_uint32
+    lib.host_model_decode_packet_total.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p, C.c_int]
     lib.host_model_check_division.restype = C.c_uint64
     lib.host_model_check_division.argtypes = [C.c_uint32, C.c_uint32]
     lib.host_model_check_renorm.restype = C.c_uint64
@@ -39,14 +43,18 @@ def model():
     return lib
 
 
-def model_encode(lib, data, packet=8192):
+def model_encode(lib, data, packet=8192, ws=False):
     buf = np.zeros(O.n_packets(data.size, packet) * (packet + 512) + 64, np.uint8)
     src = data if data.size else np.zeros(1, np.uint8)
-    return buf[: lib.host_model_encode_stream(O._ptr(src), data.size, O._ptr(buf), packet)].copy()
+    fn = lib.host_model_encode_stream_ws if ws else lib.host_model_encode_stream
+    return buf[: fn(O._ptr(src), data.size, O._ptr(buf), packet)].copy()
 
 
-def model_decode(lib, pay, n, early=False):
+def model_decode(lib, pay, n, early=False, total=False):
     fn = lib.host_model_decode_packet_early if early else lib.host_model_decode_packet
+    if total:
+        def fn(p, r, o, out, _early=int(early)):
+            return lib.host_model_decode_packet_total(p, r, o, out, _early)
     c = pay.size
     padded = np.zeros((c + 64 + 15) // 16 * 16, np.uint8)
     padded[:c] = pay
@@ -81,8 +89,11 @@ def test_kernel_math_matches_reference_golden(model, name):
     data = make_input(rec)
     pay = model_encode(model, data)
     assert pay.size == rec["payload_bytes"] and md5(pay) == rec["payload_md5"]
+    assert np.array_equal(model_encode(model, data, ws=True), pay)
     assert np.array_equal(model_decode(model, pay, data.size), data)
     assert np.array_equal(model_decode(model, pay, data.size, early=True), data)
+    assert np.array_equal(model_decode(model, pay, data.size, early=True, total=True), data)
+    assert np.array_equal(model_decode(model, pay, data.size, total=True), data)
 
 
 @pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 63, 64, 65, 4095, 8191, 8192])
@@ -90,8 +101,11 @@ def test_kernel_math_ragged_lengths(model, n):
     for data in (D.uniform(n, n), D.and3(n + 1, n), D.zeros(n), D.round_robin(n)):
         pay = model_encode(model, data)
         assert np.array_equal(pay, O.encode(data))
+        assert np.array_equal(model_encode(model, data, ws=True), pay)
         assert np.array_equal(model_decode(model, pay, n), data)
         assert np.array_equal(model_decode(model, pay, n, early=True), data)
+        assert np.array_equal(model_decode(model, pay, n, early=True, total=True), data)
+        assert np.array_equal(model_decode(model, pay, n, total=True), data)
 
 
 @pytest.mark.parametrize("packet", [4096, 12288, 16112])
@@ -101,8 +115,11 @@ def test_kernel_math_other_packet_sizes(model, packet):
     data = D.mixed(rec["seed"], rec["n"])
     pay = model_encode(model, data, packet)
     assert pay.size == rec["payload_bytes"] and md5(pay) == rec["payload_md5"]
+    assert np.array_equal(model_encode(model, data, packet, ws=True), pay)
     assert np.array_equal(model_decode(model, pay, data.size), data)
     assert np.array_equal(model_decode(model, pay, data.size, early=True), data)
+    assert np.array_equal(model_decode(model, pay, data.size, early=True, total=True), data)
+    assert np.array_equal(model_decode(model, pay, data.size, total=True), data)
 
 
 def test_kernel_math_long_underflow_runs(model):
@@ -112,4 +129,6 @@ def test_kernel_math_long_underflow_runs(model):
         data = rng.choice(np.array([127, 128], np.uint8), size=8192, p=[0.5, 0.5])
         pay = model_encode(model, data)
         assert np.array_equal(pay, O.encode(data))
+        assert np.array_equal(model_encode(model, data, ws=True), pay)
         assert np.array_equal(model_decode(model, pay, 8192), data)
+        assert np.array_equal(model_decode(model, pay, 8192, early=True, total=True), data)

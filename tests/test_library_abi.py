@@ -84,3 +84,15 @@ def test_no_device_means_error_not_fallback():
 def test_strerror():
     assert _lib.strerror(0) == "ok"
     assert "argument" in _lib.strerror(_lib.E_ARG)
+
+
+def test_options_validate_their_values():
+    """gpuar_b200_set_option: unknown keys and out-of-range values are refused (no device needed)."""
+    for key, good, bad in ((_lib.OPT_ENCODE_PATH, (0, 1, 2), (-1, 3)),
+                           (_lib.OPT_COMPACT_TILE, (4, 8, 16, 32, 64, 128, 0), (-4, 2, 3, 24, 256)),
+                           (_lib.OPT_WS_MAX_PACKETS, (0, 23680), (-1,))):
+        for v in bad:
+            assert _lib.lib().gpuar_b200_set_option(key, v) == _lib.E_ARG, (key, v)
+        for v in good:
+            assert _lib.lib().gpuar_b200_set_option(key, v) == 0, (key, v)
+    assert _lib.lib().gpuar_b200_set_option(99, 0) == _lib.E_ARG
