@@ -99,12 +99,19 @@ GPUAR_HD void narrow_renorm(uint32_t &L, uint32_t &V, uint32_t lo, uint32_t hi, 
 // State here is (L, R) with R = range = upper - lower + 1 carried explicitly.  The recurrence
 // only needs the TOTAL shift t = k + u, and t follows from the WIDTH W = U1 - L1 + 1 of the
 // narrowed interval up to one position: the renormalised width W * 2^t lies in (2^14, 2^16],
-// so with e = floor(log2(W - 1)) (e = -1 for W = 1) t is 14 - e or 15 - e.  Shift by
-// s1 = 15 - e and look at the two top bit pairs of the 17-bit frame (L1 and U1 carry a
-// leading 0, so the inverted upper bound Vx carries a leading 1 -- s1 = 0 then falls out as
-// "MSBs equal"): the last shift is due exactly when the MSBs (bit 16) are equal, or the next
-// bits (bit 15) read L = 1, U = 0 (underflow).  Otherwise one shift less.  Every shift
-// doubles the width exactly, so R = W << t needs neither L nor the upper bound.
+// so with e = floor(log2(W - 1)) (e = -1 for W = 1) t is 14 - e or 15 - e.  Every shift
+// doubles the width exactly, so the new range is W << t and needs neither bound.
+//
+// Which of the two: shift by s1 = 15 - e.  A = L1 << s1 is the lower bound in a 17-bit frame
+// (bits above 16 are the bits already gone), R1 = W << s1 lies in (2^15, 2^16], and the
+// upper bound is A + R1 - 1.  R1 - 1 lies in [2^15, 2^16), so going from A to the upper bound
+// advances the two-bit number formed by frame bits 16 and 15 by one, plus the carry out of
+// the low 15 bits.  Advancing by one always leaves top bits that ask for the last shift --
+// (0,1) and (2,3) have equal MSBs, (1,2) and (3,0) show the underflow pattern L = 1, U = 0 in
+// the second bits -- and advancing by two never does: (0,2), (1,3), (2,0), (3,1) have
+// different MSBs and equal second bits.  So "one shift less" IS that carry:
+//     sx = ((A & 0x7FFF) + R1 - 0x8001) >> 15;   t = s1 - sx;   R = R1 >> sx;
+//     L = (A >> sx) & 0x7FFF;   and bit 15 of A >> sx tells whether u != 0.
 //
 // e comes from the exponent of a float, built with one integer add and one float subtract,
 // so no count-leading-zeros or conversion instruction -- both variable-latency on the XU
@@ -139,88 +146,51 @@ GPUAR_HD uint32_t funnel_r_wrap(uint32_t lo, uint32_t hi, uint32_t s)    // low 
     return (uint32_t)((((uint64_t)hi << 32) | lo) >> (s & 31u));
 #endif
 }
-// x >> 1 that the compiler may not fold into the select that follows it: both candidates of
-// narrow_total must exist BEFORE the decision, or they land back on the dependent chain.
-GPUAR_HD uint32_t half_eager(uint32_t x)
-{
-#if defined(__CUDA_ARCH__)
-    uint32_t r;
-    asm volatile("shr.b32 %0, %1, 1;" : "=r"(r) : "r"(x));
-    return r;
-#else
-    return x >> 1;
-#endif
-}
-GPUAR_HD bool last_shift_due(uint32_t A, uint32_t B)          // MSBs (bit 16) equal, or bit 15: L = 1, U = 0
-{
-#if defined(__CUDA_ARCH__)
-    uint32_t x, y;
-    asm("lop3.b32 %0, %1, %2, 0x10000, 0x28;" : "=r"(x) : "r"(A), "r"(B));   // (A ^ B) & bit 16
-    asm("lop3.b32 %0, %1, %2, 0x8000, 0x80;" : "=r"(y) : "r"(A), "r"(B));    // A & B & bit 15
-    return (x | y) != 0u;
-#else
-    return (((A ^ B) & 0x10000u) | (A & B & 0x8000u)) != 0u;
-#endif
-}
 
 //   in : L, R; lo = cum[s], hi = cum[s+1]; (m, sh) for the current total
-//   out: L, R renormalised; L1 = lower bound and Vx = 0x1FFFF - upper bound before
-//        renormalisation; t = total shift (0..16); As = L1 << t with bit 15 kept
-//        (bit 15 set <=> u != 0)
+//   out: L, R renormalised; L1 = lower bound and S1 = upper bound + 1 before renormalisation;
+//        t = total shift (0..16); As = L1 << t with bit 15 kept (bit 15 set <=> u != 0)
 GPUAR_HD void narrow_total(uint32_t &L, uint32_t &R, uint32_t lo, uint32_t hi, uint32_t m, uint32_t sh,
-                           uint32_t &L1, uint32_t &Vx, uint32_t &t, uint32_t &As)
+                           uint32_t &L1, uint32_t &S1, uint32_t &t, uint32_t &As)
 {
     const uint32_t qa = div_total(hi * R, m, sh);
     const uint32_t qb = div_total(lo * R, m, sh);
     const uint32_t E = width_exponent(qa, qb);                // = 16 - s1 (mod 32)
     L1 = L + qb;
-    Vx = 0x20000u - L - qa;                                   // bit 16 always set
+    S1 = L + qa;
     const uint32_t A = funnel_r_wrap(L1 << 16, 0u, E);        // L1 << s1
-    const uint32_t B = funnel_r_wrap(Vx << 16, 1u, E);        // Vx << s1
     const uint32_t R1 = funnel_r_wrap((qa - qb) << 16, 0u, E);
-    const uint32_t R0 = half_eager(R1), A0 = half_eager(A);
-    const bool last = last_shift_due(A, B);
-    R = last ? R1 : R0;
-    As = last ? A : A0;
+    const uint32_t sx = ((A & 0x7FFFu) + R1 - 0x8001u) >> 15; // carry out of the low 15 bits (sum < 2^16)
+    R = R1 >> sx;
+    As = A >> sx;
     L = As & 0x7FFFu;
-    t = (last ? 16u : 15u) - (E & 31u);
+    t = 16u - (E & 31u) - sx;
 }
 
 // The encoder's CODER warp goes one step further and never applies the decision to the
-// range at all: it carries R1 = W << s1 (always in (2^15, 2^16]) together with the pending
-// halving sx = 1 - last, and the next step divides with sx added to the shift of the
-// reciprocal division: floor(c * (R1 >> sx) / T) = floor(floor(c * R1 / T) >> sx), R1 being
-// even whenever sx = 1.  The products and the multiply-high of the next step then start from
-// R1 directly, in parallel with the decision, and the decision itself is integer arithmetic
-// (no predicate, whose write-to-use latency is several times that of a register).
+// range at all: it carries R1 together with the pending halving sx, and the next step
+// divides with sx added to the shift of the reciprocal division:
+// floor(c * (R1 >> sx) / T) = floor(floor(c * R1 / T) >> sx), R1 being even whenever sx = 1
+// (sx = 1 needs s1 >= 1).  The products and the multiply-high of the next step then start
+// from R1 directly, in parallel with the decision.
 //   state: L (15 bit), R1, sx;  true range = R1 >> sx.   Start: L = 0, R1 = 65536, sx = 0.
+//   out  : L1 = lower bound, S1 = upper bound + 1, both before renormalisation
 GPUAR_HD void narrow_lazy(uint32_t &L, uint32_t &R1, uint32_t &sx, uint32_t lo, uint32_t hi, uint32_t m,
-                          uint32_t sh, uint32_t &L1, uint32_t &Vx)
+                          uint32_t sh, uint32_t &L1, uint32_t &S1)
 {
     const uint32_t qa = (mulhi32(hi * R1, m) >> sh) >> sx;
     const uint32_t qb = (mulhi32(lo * R1, m) >> sh) >> sx;
     const uint32_t E = width_exponent(qa, qb);
     L1 = L + qb;
-    Vx = 0x20000u - L - qa;
-    const uint32_t A = funnel_r_wrap(L1 << 16, 0u, E), B = funnel_r_wrap(Vx << 16, 1u, E);      // << s1
-    const uint32_t A0 = funnel_r_wrap(L1 << 15, 0u, E), B0 = funnel_r_wrap(Vx << 15, 0u, E);    // << (s1 - 1)
+    S1 = L + qa;
+    const uint32_t A = funnel_r_wrap(L1 << 16, 0u, E);        // L1 << s1
     R1 = funnel_r_wrap((qa - qb) << 16, 0u, E);
-    // bit 15 of the half frame = bit 16 of the full one: MSBs equal <=> L and inverted U differ there
-#if defined(__CUDA_ARCH__)
-    uint32_t x, y, nz;                                        // three-input logic ops, two levels
-    asm("lop3.b32 %0, %1, %2, 0x8000, 0x28;" : "=r"(x) : "r"(A0), "r"(B0));       // (A0 ^ B0) & bit 15
-    asm("lop3.b32 %0, %1, %2, 0x8000, 0x80;" : "=r"(y) : "r"(A), "r"(B));         // A & B & bit 15
-    asm("lop3.b32 %0, %1, %2, 0x8000, 0x56;" : "=r"(nz) : "r"(x), "r"(y));        // (x | y) ^ bit 15
-    sx = nz >> 15;
-#else
-    sx = ((((A0 ^ B0) & 0x8000u) | (A & B & 0x8000u)) ^ 0x8000u) >> 15;
-#endif
+    sx = ((A & 0x7FFFu) + R1 - 0x8001u) >> 15;                // carry out of the low 15 bits (sum < 2^16)
     L = (A >> sx) & 0x7FFFu;
 }
 
-// L1 | U1 << 16 from L1 and Vx = 0x1FFFF - U1 (bit 16 set), as two multiply-adds:
-// U1 << 16 = -(Vx + 1) << 16 modulo 2^32.
-GPUAR_HD uint32_t pack_bounds(uint32_t L1, uint32_t Vx) { return Vx * 0xFFFF0000u + (L1 - 0x10000u); }
+// L1 | U1 << 16 from L1 and S1 = U1 + 1, as two multiply-adds
+GPUAR_HD uint32_t pack_bounds(uint32_t L1, uint32_t S1) { return S1 * 0x10000u + (L1 - 0x10000u); }
 
 // ---- encoder bit sink: MSB-first stream (gpuar_kernel.cu:128-151), flushed as 32-bit words.
 // Branch free: after appending, at most one whole word is ready; it is stored under a

@@ -152,8 +152,8 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
                                : tree_decode(root, tree, 32u, unscale_range(code, L, range, T), T, lo, cnt);
         packed |= s << (8u * slot);
         if (kTotal) {
-            uint32_t L1, Vx, t, As;
-            narrow_total(L, V, lo, lo + cnt, m, sh, L1, Vx, t, As);
+            uint32_t L1, S1, t, As;
+            narrow_total(L, V, lo, lo + cnt, m, sh, L1, S1, t, As);
             code = advance_code_total(code, t, As, in);
         } else {
             uint32_t k, u, U1;

@@ -175,9 +175,9 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
                     }
 #pragma unroll
                     for (uint32_t j = 0; j < kCoderBlock; ++j) {
-                        uint32_t L1, Vx;
-                        narrow_lazy(L, R1, sx, lo[j], hi[j], m[j], sh, L1, Vx);
-                        sm.ring_c[b][j0 + j][lane] = pack_bounds(L1, Vx);
+                        uint32_t L1, S1;
+                        narrow_lazy(L, R1, sx, lo[j], hi[j], m[j], sh, L1, S1);
+                        sm.ring_c[b][j0 + j][lane] = pack_bounds(L1, S1);
                     }
                 }
             } else {
@@ -188,9 +188,9 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
                     const uint32_t lo = sm.ring_a[b][j][lane] + sm.ring_b[b][j][lane] + (pd & 0xFFFFu);
                     uint32_t c = 0;
                     if (i0 + j < len) {
-                        uint32_t L1, Vx;
-                        narrow_lazy(L, R1, sx, lo, lo + (pd >> 16), m, sh, L1, Vx);
-                        c = pack_bounds(L1, Vx);
+                        uint32_t L1, S1;
+                        narrow_lazy(L, R1, sx, lo, lo + (pd >> 16), m, sh, L1, S1);
+                        c = pack_bounds(L1, S1);
                     }
                     sm.ring_c[b][j][lane] = c;
                 }

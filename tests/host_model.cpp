@@ -55,7 +55,7 @@ uint32_t host_model_encode_packet_ws(const uint8_t *x, uint32_t n, uint8_t *slot
     for (uint32_t i = 0; i < n; ++i) {
         uint32_t sh;
         const uint32_t m = magic_for(256u + i, sh);
-        uint32_t cnt, L1, Vx, k, u;
+        uint32_t cnt, L1, S1, k, u;
         // the model warps take their symbols four at a time from one input word
         uint32_t word = 0;
         memcpy(&word, x + (i & ~3u), (n - (i & ~3u)) < 4u ? (n - (i & ~3u)) : 4u);
@@ -64,8 +64,8 @@ uint32_t host_model_encode_packet_ws(const uint8_t *x, uint32_t n, uint8_t *slot
         const uint32_t lo_d = tree_encode_leaf_word(tree.data(), 1, word_fields_leaf(word), i & 3u, cnt);
         const uint32_t pd = cnt * 65536u + lo_d;
         const uint32_t lo = pa + pb + (pd & 0xFFFFu);
-        narrow_lazy(L, R, sx, lo, lo + (pd >> 16), m, sh, L1, Vx);
-        const uint32_t c = pack_bounds(L1, Vx);                    // ring C entry
+        narrow_lazy(L, R, sx, lo, lo + (pd >> 16), m, sh, L1, S1);
+        const uint32_t c = pack_bounds(L1, S1);                    // ring C entry
         const uint32_t U1 = c >> 16;
         shifts_of(c & 0xFFFFu, U1, k, u);
         emit_packed_any(out, pend, pack_field(k, u, c));
@@ -141,8 +141,8 @@ static uint32_t decode_packet(const uint8_t *payload, size_t readable, size_t of
                                  : tree_decode(root, tree.data(), 1, unscale_range(code, L, range, T), T, lo, cnt);
         out[i] = (uint8_t)s;
         if (total) {
-            uint32_t L1, Vx, t, As;
-            narrow_total(L, V, lo, lo + cnt, m, sh, L1, Vx, t, As);
+            uint32_t L1, S1, t, As;
+            narrow_total(L, V, lo, lo + cnt, m, sh, L1, S1, t, As);
             code = advance_code_total(code, t, As, in);
         } else {
             uint32_t k, u, U1;
@@ -225,18 +225,19 @@ uint64_t host_model_check_renorm(uint64_t seed, uint32_t count, uint32_t packet)
         narrow_renorm(L, V, cl, ch, m, sh, k, u, U1);
         bad += (L != Lr) || ((V ^ 0xFFFFu) != U) || (k != kk) || (u != uu) || (U1 != U1ref);
         // the single-normalisation form of the same step (narrow_total + shifts_of)
-        uint32_t L2 = lo16, R2 = hi16 - lo16 + 1u, L1, Vx, t, As, k2, u2;
-        narrow_total(L2, R2, cl, ch, m, sh, L1, Vx, t, As);
-        const uint32_t U1b = (~Vx) & 0xFFFFu;
+        uint32_t L2 = lo16, R2 = hi16 - lo16 + 1u, L1, S1, t, As, k2, u2;
+        narrow_total(L2, R2, cl, ch, m, sh, L1, S1, t, As);
+        const uint32_t U1b = S1 - 1u;
         shifts_of(L1, U1b, k2, u2);
         bad += (L2 != Lr) || (R2 != (uint32_t)U - Lr + 1u) || (U1b != U1ref) || (k2 != kk) || (u2 != uu);
         bad += (t != kk + uu) || (((As >> 15) & 1u) != (uu ? 1u : 0u));
         // and the lazy form, entered with the range held as is (sx = 0) or doubled (sx = 1)
         for (uint32_t pre = 0; pre < 2u; ++pre) {
-            uint32_t L3 = lo16, R3 = (hi16 - lo16 + 1u) << pre, s3 = pre, L1c, Vxc;
-            narrow_lazy(L3, R3, s3, cl, ch, m, sh, L1c, Vxc);
-            bad += (L3 != Lr) || ((R3 >> s3) != (uint32_t)U - Lr + 1u) || (L1c != L1) || (Vxc != Vx) ||
-                   (s3 && (R3 & 1u)) || R3 <= 32768u || R3 > 65536u;
+            uint32_t L3 = lo16, R3 = (hi16 - lo16 + 1u) << pre, s3 = pre, L1c, S1c;
+            narrow_lazy(L3, R3, s3, cl, ch, m, sh, L1c, S1c);
+            bad += (L3 != Lr) || ((R3 >> s3) != (uint32_t)U - Lr + 1u) || (L1c != L1) || (S1c != U1ref + 1u) ||
+                   (s3 && (R3 & 1u)) || R3 <= 32768u || R3 > 65536u ||
+                   pack_bounds(L1c, S1c) != (L1 | ((uint32_t)U1ref << 16));
         }
     }
     return bad;
