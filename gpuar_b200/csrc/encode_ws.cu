@@ -19,7 +19,7 @@
 // Each warp keeps lane = packet, so per-packet state never crosses lanes; the rings are
 // double buffered per round of 32 positions and handed over with named barriers
 // (bar.arrive on the producer side, bar.sync on the consumer side).  The three model rings
-// share one full/empty barrier pair per buffer (128 threads: three producers + CODER).
+// share one full barrier per buffer (128 threads: three producers + CODER).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -48,8 +48,13 @@ struct WsShared {
     uint32_t final_l[32];                // CODER -> BITS at the end of the packet
 };
 
-// named barriers (0 is __syncthreads); id + buffer index
-enum : uint32_t { kInFull = 1, kInEmpty = 3, kCFull = 5, kCEmpty = 7, kFFull = 9, kFEmpty = 11, kDone = 13 };
+// Named barriers, id + buffer index; all sixteen are in use (the kernel has no __syncthreads,
+// so barrier 0 is free).  A "full" barrier is arrived at by the producer(s) and waited on by the
+// one consumer; an "empty" barrier the other way round.  The three model rings share their full
+// barrier (three producers + CODER = 128 threads) but are handed back one by one, so that
+// every barrier has exactly one waiting warp (which is also what compute-sanitizer's synccheck
+// expects: it reports warps that wait on one barrier from different instructions as divergent).
+enum : uint32_t { kInFull = 0, kInEmpty = 2 /* + 2 * role */, kCFull = 8, kCEmpty = 10, kFFull = 12, kFEmpty = 14 };
 constexpr uint32_t kInCount = 128;       // MODEL-A, MODEL-B, MODEL-D, CODER
 constexpr uint32_t kPairCount = 64;      // one producer warp + one consumer warp
 
@@ -59,10 +64,15 @@ __device__ __forceinline__ void bar_sync(uint32_t id)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kCount) : "memory");
 }
 template <uint32_t kCount>
+__device__ __forceinline__ void bar_arrive_raw(uint32_t id)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kCount) : "memory");
+}
+template <uint32_t kCount>
 __device__ __forceinline__ void bar_arrive(uint32_t id)
 {
-    __threadfence_block();                                       // ring writes visible before the hand-over
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kCount) : "memory");
+    __threadfence_block();                                       // ring accesses ordered before the hand-over
+    bar_arrive_raw<kCount>(id);
 }
 
 // kRole 0: root + level 1 -> ring A;  1: level 2 -> ring B;  2: leaves -> ring D.
@@ -105,7 +115,7 @@ __device__ __forceinline__ void model_warp(WsShared &sm, uint64_t *tree, const u
         stage[4][lane] = buf_b.x, stage[5][lane] = buf_b.y, stage[6][lane] = buf_b.z, stage[7][lane] = buf_b.w;
         buf_a = fetch(2u * r + 2u);
         buf_b = fetch(2u * r + 3u);
-        if (r >= 2u) bar_sync<kInCount>(kInEmpty + b);
+        if (r >= 2u) bar_sync<kPairCount>(kInEmpty + 2u * kRole + b);
         if (i0 + kRound <= min_len) {
 #pragma unroll 1
             for (uint32_t w = 0; w < 8u; ++w) {
@@ -195,11 +205,14 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
                     sm.ring_c[b][j][lane] = c;
                 }
             }
-            if (r + 2u < rounds) bar_arrive<kInCount>(kInEmpty + b);
+            if (r + 2u < rounds) {                                 // the buffer goes back to the three model warps
+                bar_arrive<kPairCount>(kInEmpty + b);
+                bar_arrive_raw<kPairCount>(kInEmpty + 2u + b);
+                bar_arrive_raw<kPairCount>(kInEmpty + 4u + b);
+            }
+            if (r + 1u == rounds) sm.final_l[lane] = L;            // reaches BITS through the two hand-overs below
             bar_arrive<kPairCount>(kCFull + b);
         }
-        sm.final_l[lane] = L;
-        bar_arrive<kPairCount>(kDone);
     } else if (role == 3u) {
         // ------------------------------------------------------------ FIELD (stateless)
         for (uint32_t r = 0; r < rounds; ++r) {
@@ -283,7 +296,8 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
             }
             if (r + 2u < rounds) bar_arrive<kPairCount>(kFEmpty + b);
         }
-        bar_sync<kPairCount>(kDone);
+        // final_l: written by CODER before its last "C full", which FIELD waited for before its last
+        // "F full", which this warp waited for in the last round (release/acquire chain at CTA scope)
         if (mine) {
             const uint32_t comp = finish_packet(out, sm.final_l[lane], pend, slot, len);
             if (sizes) sizes[my] = comp;
