@@ -82,7 +82,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -90,7 +90,18 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def wait_first(self, timeout=3.0):
+        """Blocks until nvidia-smi has printed its first row; rows up to here (idle GPU) are dropped."""
+        t_end = time.perf_counter() + timeout
+        while self.proc and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.005)
+        self.t_load = time.perf_counter()
+
+    def mark(self):
+        """Start of the timed region: samples before it (warm-up, same kernels) are kept apart."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -100,21 +111,24 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
-            if len(r) < 6:
+        sm, mx, reasons, inside = [], None, set(), 0
+        for t, r in self.rows:
+            if len(r) < 6 or t < getattr(self, "t_load", 0.0):
                 continue
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
             except ValueError:
                 continue
+            inside += t >= getattr(self, "t_mark", 0.0)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
+        # the sampler runs from the warm-up on (the same kernels, back to back); `samples_timed` of them
+        # fall inside the timed region, which at 64 MiB lasts only a few tens of milliseconds
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "samples_timed": inside}
 
 
 # =============================================================== reference arm
@@ -320,6 +334,10 @@ def run_ours(args):
         return sum(a.elapsed_time(b) for a, b in evs) / 1e3
 
     # ---- warm-up (>= 3) and correctness gate: nothing is reported unless the round trip holds
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first()                      # nvidia-smi is looping from here on
     for _ in range(max(3, args.warmup)):
         enc_step()
     torch.cuda.synchronize()
@@ -327,13 +345,17 @@ def run_ours(args):
     c_holder[0] = c
     for _ in range(max(3, args.warmup)):
         dec_step()
+    # a 64 MiB step lasts ~3 ms: keep the same kernels running (untimed) for ~0.2 s so that the sampler
+    # sees the load; the count depends on the size only, so every rank does the same (enc_step is collective)
+    for _ in range(max(3, min(100, int(0.2 / (nbytes / 30e9))))):
+        enc_step()
+        dec_step()
+    torch.cuda.synchronize()
     torch.cuda.synchronize()
     assert [int(v) for v in result.tolist()[:3]] == [packets, nbytes, 0], result.tolist()
     assert torch.equal(out[:nbytes], x), "decode(encode(x)) != x"
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     launches0 = _lib.launch_count()
     _lib.profile(True)
     _lib.profile_read()

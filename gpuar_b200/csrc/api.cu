@@ -41,8 +41,10 @@ static int ck(cudaError_t e) { return (int)e; }
 
 // ---- tuning knobs (gpuar_b200_set_option)
 static int g_encode_path = 0;                    // 0 auto, 1 fused lane=packet, 2 warp-specialised
-// auto: the warp-specialised kernel while the input is at most one resident wave of its CTAs
-static size_t g_ws_max_packets = (size_t)148 * 3 * 32;   // three 62.6 KB CTAs fit one SM: one resident wave
+// auto: the warp-specialised kernel up to two resident waves of its CTAs (three 74 KB CTAs fit one
+// SM).  Measured crossover with the lane=packet kernel on B200: 192 MiB 1.74 vs 1.92 ms, 256 MiB
+// 2.05 vs 1.94 ms (profiles/r1_end_work_unit_and_size_sweep.jsonl).
+static size_t g_ws_max_packets = (size_t)148 * 3 * 32 * 2;
 
 static cudaError_t encode_slots(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t stride, uint32_t *d_sizes,
                                 uint32_t packet, cudaStream_t st)

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kWsThreads)
 encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ slots, uint32_t slot_stride,
                  uint32_t *__restrict__ sizes, uint32_t n_packets, uint32_t packet)
 {
-    extern __shared__ __align__(16) uint8_t ws_smem[];           // 62.6 KB: above the static limit
+    extern __shared__ __align__(16) uint8_t ws_smem[];           // 72 KB: above the static limit
     WsShared &sm = *reinterpret_cast<WsShared *>(ws_smem);
     const uint32_t lane = lane_id();
     const uint32_t role = threadIdx.x >> 5;
