@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -101,11 +102,15 @@ struct DeviceBuf {
         return e;
     }
 };
-constexpr int kLanes = 8;                        // chunks in flight in the host-buffer pipelines
+constexpr int kLanes = 16;                       // chunks in flight in the host-buffer pipelines
 struct HostPath {
     int device = -1;
     cudaStream_t stream[kLanes] = {}, copy = nullptr;
-    cudaEvent_t done[kLanes] = {}, ready = nullptr;
+    // All host->device copies go through `up` and all device->host copies through `down`, in chunk
+    // order: copies issued on different streams share the link in time slices, so that every chunk
+    // arrives late; in order, chunk k is complete after (k+1)/chunks of the transfer time.
+    cudaStream_t up = nullptr, down = nullptr;
+    cudaEvent_t done[kLanes] = {}, arrived[kLanes] = {}, drained[kLanes] = {}, ready = nullptr;
     DeviceBuf in[kLanes], pay[kLanes], scratch[kLanes];
     DeviceBuf big_in, big_out, big_scratch, offsets, result;
     uint64_t *h_total = nullptr;                 // pinned: per-lane payload totals
@@ -114,6 +119,13 @@ struct HostPath {
 };
 static std::mutex g_mu;
 static std::vector<HostPath *> g_paths;
+
+// tuning aid: GPUAR_B200_HOST_CHUNKS=<n> overrides the chunk count of the host-buffer pipelines
+static size_t host_chunks(size_t dflt)
+{
+    static const long v = [] { const char *e = getenv("GPUAR_B200_HOST_CHUNKS"); return e ? atol(e) : 0L; }();
+    return v > 0 ? (size_t)v : dflt;
+}
 
 static int host_path(HostPath **out)
 {
@@ -127,7 +139,11 @@ static int host_path(HostPath **out)
     for (int i = 0; i < kLanes; ++i) {
         if ((e = cudaStreamCreateWithFlags(&h->stream[i], cudaStreamNonBlocking)) != cudaSuccess) return ck(e);
         if ((e = cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming)) != cudaSuccess) return ck(e);
+        if ((e = cudaEventCreateWithFlags(&h->arrived[i], cudaEventDisableTiming)) != cudaSuccess) return ck(e);
+        if ((e = cudaEventCreateWithFlags(&h->drained[i], cudaEventDisableTiming)) != cudaSuccess) return ck(e);
     }
+    if ((e = cudaStreamCreateWithFlags(&h->up, cudaStreamNonBlocking)) != cudaSuccess) return ck(e);
+    if ((e = cudaStreamCreateWithFlags(&h->down, cudaStreamNonBlocking)) != cudaSuccess) return ck(e);
     if ((e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking)) != cudaSuccess) return ck(e);
     if ((e = cudaEventCreateWithFlags(&h->ready, cudaEventDisableTiming)) != cudaSuccess) return ck(e);
     if ((e = cudaMallocHost(&h->h_total, (kLanes + 8) * sizeof(uint64_t))) != cudaSuccess) return ck(e);
@@ -341,16 +357,17 @@ int gpuar_b200_compress_host(const uint8_t *in, size_t n, uint8_t *gip, size_t g
     int rc = host_path(&h);
     if (rc) return rc;
 
-    // chunks rotate over kLanes streams: H2D, encode and scan+compact of chunk k overlap the D2H
-    // of earlier chunks; the host only waits for the 8-byte total of a chunk to know where the
-    // next one lands in the image.  A chunk's kernels take about the same time from 1 to ~20 000
-    // packets (a packet is a serial chain of 8192 steps), so the end-to-end time is roughly
-    // H2D(everything) + one kernel latency + D2H(last chunk): small inputs use many small chunks
-    // to shorten that tail, large ones 64 MiB chunks to keep enough packets in flight.
-    // No more chunks than lanes while the input is small: a lane is only reused after its chunk
-    // has finished, which would stall the H2D stream for a kernel latency.
-    size_t chunk = align_up(n / kLanes + 1, kPacket);
-    chunk = chunk < ((size_t)4 << 20) ? ((size_t)4 << 20) : chunk > ((size_t)64 << 20) ? ((size_t)64 << 20) : chunk;
+    // Chunks rotate over kLanes sets of device buffers: the input of chunk k travels on the `up`
+    // stream, its kernels run on lane k % kLanes, its payload leaves on the `down` stream; the host
+    // only waits for the 8-byte total of a chunk (written by the compaction kernel straight into
+    // pinned memory) to know where the next one lands in the image.  A chunk's kernels take about
+    // the same time from 1 to ~10 000 packets (a packet is a serial chain of 8192 steps), so the
+    // end-to-end time is roughly H2D(everything) + one kernel latency + D2H(last chunk): small
+    // inputs are cut into kLanes chunks to shorten that tail (2..32 measured at 64 MiB with
+    // tools/e2e_timeline.cu and tools/e2e_sweep.py: flat from 8 to 16, worse outside), large ones
+    // into 64 MiB chunks to keep enough packets in flight.
+    size_t chunk = align_up(n / host_chunks(kLanes) + 1, kPacket);
+    chunk = chunk < ((size_t)2 << 20) ? ((size_t)2 << 20) : chunk > ((size_t)64 << 20) ? ((size_t)64 << 20) : chunk;
     const size_t chunks = (n + chunk - 1) / chunk;
     size_t pos = GPUAR_FILE_HEADER;
     cudaError_t e = cudaSuccess;
@@ -359,7 +376,8 @@ int gpuar_b200_compress_host(const uint8_t *in, size_t n, uint8_t *gip, size_t g
         cudaError_t er = cudaEventSynchronize(h->done[l]);
         if (er != cudaSuccess) return er;
         const size_t bytes = (size_t)h->h_total[l];
-        er = cudaMemcpyAsync(gip + pos, h->pay[l].p, bytes, cudaMemcpyDeviceToHost, h->stream[l]);
+        er = cudaMemcpyAsync(gip + pos, h->pay[l].p, bytes, cudaMemcpyDeviceToHost, h->down);
+        if (er == cudaSuccess) er = cudaEventRecord(h->drained[l], h->down);
         pos += bytes;
         return er;
     };
@@ -367,25 +385,29 @@ int gpuar_b200_compress_host(const uint8_t *in, size_t n, uint8_t *gip, size_t g
         const int l = (int)(k % kLanes);
         const size_t off = k * chunk, m = (n - off < chunk) ? n - off : chunk;
         const EncodePlan p = encode_plan(m);
-        if (k >= (size_t)kLanes) e = drain(k - kLanes);            // frees lane l's buffers (stream order)
+        cudaStream_t st = h->stream[l];
+        if (k >= (size_t)kLanes) {
+            // lane l is reused: its input buffer is free (the host has seen done[l]), its payload
+            // and scratch once the copy of the previous occupant has left
+            e = drain(k - kLanes);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->drained[l], 0);
+        }
         if (e == cudaSuccess) e = h->in[l].need(align_up(m, 16) + 16);
         if (e == cudaSuccess) e = h->pay[l].need(gpuar_b200_payload_bound(m) + 16);
         if (e == cudaSuccess) e = h->scratch[l].need(p.total);
         if (e != cudaSuccess) break;
-        cudaStream_t st = h->stream[l];
-        e = cudaMemcpyAsync(h->in[l].p, in + off, m, cudaMemcpyHostToDevice, st);
+        e = cudaMemcpyAsync(h->in[l].p, in + off, m, cudaMemcpyHostToDevice, h->up);
+        if (e == cudaSuccess) e = cudaEventRecord(h->arrived[l], h->up);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->arrived[l], 0);
         if (e != cudaSuccess) break;
-        uint64_t *d_total = reinterpret_cast<uint64_t *>(static_cast<uint8_t *>(h->pay[l].p) +
-                                                         gpuar_b200_payload_bound(m));
-        rc = gpuar_b200_encode((const uint8_t *)h->in[l].p, m, (uint8_t *)h->pay[l].p, h->pay[l].cap, d_total,
-                               nullptr, h->scratch[l].p, h->scratch[l].cap, st);
+        rc = gpuar_b200_encode((const uint8_t *)h->in[l].p, m, (uint8_t *)h->pay[l].p, h->pay[l].cap,
+                               &h->h_total[l], nullptr, h->scratch[l].p, h->scratch[l].cap, st);
         if (rc) return rc;
-        e = cudaMemcpyAsync(&h->h_total[l], d_total, 8, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaEventRecord(h->done[l], st);
+        e = cudaEventRecord(h->done[l], st);
     }
     for (size_t k = (chunks > (size_t)kLanes ? chunks - kLanes : 0); k < chunks && e == cudaSuccess; ++k)
         e = drain(k);
-    for (int l = 0; l < kLanes && e == cudaSuccess; ++l) e = cudaStreamSynchronize(h->stream[l]);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->down);
     if (e != cudaSuccess) return ck(e);
     gpuar_b200_write_header(gip, n, pos);
     *gip_bytes = pos;
@@ -416,7 +438,7 @@ int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *ou
     cudaError_t e = h->big_in.need(align_up(c, 16) + GPUAR_PAD_BYTES + 16);
     if (e != cudaSuccess) return ck(e);
     uint8_t *d_pay = (uint8_t *)h->big_in.p;
-    size_t chunk_bytes = c / kLanes + 1;                             // payload bytes per chunk, before rounding to packets
+    size_t chunk_bytes = c / host_chunks(kLanes) + 1;                    // payload bytes per chunk, before rounding to packets
     if (chunk_bytes < ((size_t)2 << 20)) chunk_bytes = (size_t)2 << 20;
     if (chunk_bytes > ((size_t)256 << 20)) chunk_bytes = (size_t)256 << 20;
 
@@ -452,24 +474,37 @@ int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *ou
         if (status) break;
         const size_t m = packets - p0;
         if (!m) break;
-        cudaStream_t st = h->stream[lane % kLanes];
+        const int l = (int)(lane % kLanes);
+        cudaStream_t st = h->stream[l];
         ++lane;
         if (lane == 1) e = cudaSuccess; else e = cudaStreamWaitEvent(st, h->ready, 0);   // padding is in place
-        // H2D of this chunk's bytes (rounded out to 16) and of its offsets, decode, D2H
+        // H2D of this chunk's bytes (rounded out to 16) and of its offsets on the `up` stream (in
+        // chunk order), decode on the lane's stream, D2H on the `down` stream
         const size_t a16 = a & ~(size_t)15, b16 = align_up(pos, 16) < c ? align_up(pos, 16) : c;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_pay + a16, pay + a16, b16 - a16, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_pay + a16, pay + a16, b16 - a16, cudaMemcpyHostToDevice, h->up);
         uint64_t *d_off = (uint64_t *)h->offsets.p + p0;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, h->h_offsets + p0, m * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(d_off, h->h_offsets + p0, m * sizeof(uint64_t), cudaMemcpyHostToDevice, h->up);
+        if (e == cudaSuccess) e = cudaEventRecord(h->arrived[l], h->up);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->arrived[l], 0);
         if (e != cudaSuccess) return ck(e);
         uint8_t *d_out = (uint8_t *)h->big_out.p + p0 * kPacket;
         rc = gpuar_b200_decode(d_pay, c, d_off, m, d_out, m * (size_t)kPacket, st);
         if (rc) return rc;
         const size_t lo = p0 * kPacket, hi = (lo + m * kPacket < total) ? lo + m * kPacket : total;
-        e = cudaMemcpyAsync(out + lo, d_out, hi - lo, cudaMemcpyDeviceToHost, st);
+        e = cudaEventRecord(h->done[l], st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->down, h->done[l], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out + lo, d_out, hi - lo, cudaMemcpyDeviceToHost, h->down);
         if (e != cudaSuccess) return ck(e);
     }
     for (int l = 0; l < kLanes; ++l) {
         cudaError_t es = cudaStreamSynchronize(h->stream[l]);
+        if (e == cudaSuccess) e = es;
+    }
+    {
+        cudaError_t es = cudaStreamSynchronize(h->up);
+        if (e == cudaSuccess) e = es;
+        es = cudaStreamSynchronize(h->down);
         if (e == cudaSuccess) e = es;
     }
     if (status) return status;
