@@ -30,4 +30,4 @@ done
 tail -2 gpurun_out/${tag}_pytest.log
 python tools/bench_brief.py gpurun_out/${tag}_bench_u64m.json gpurun_out/${tag}_bench_s1g.json gpurun_out/${tag}_bench_m2g.json
 tail -3 gpurun_out/${tag}_bench.err
-tail -2 gpurun_out/${tag}_sanitizer_*.txt
+for f in gpurun_out/${tag}_sanitizer_*.txt; do tail -n 2 $f; done
