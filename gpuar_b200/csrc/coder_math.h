@@ -461,10 +461,15 @@ GPUAR_HD uint32_t tree_decode_early_range(uint64_t &root, uint64_t *nodes, uint3
                                           uint32_t L, uint32_t range, uint32_t T, uint32_t &lo, uint32_t &cnt)
 {
     const uint32_t num = (((code - L) & 0xFFFFu) + 1u) * T - 1u;
+    // "threshold * range <= num" as the sign of num - threshold * range (everything < 2^30): one
+    // multiply-add and one shift per threshold, no predicates (their write-to-use latency is
+    // several times that of a register, and turning them into numbers costs a select each)
+    const uint32_t nr = 0u - range;
+    auto above = [](uint32_t d) { return d >> 31; };               // 1 if the threshold lies above the target
     // level 0
     const uint32_t r0 = (uint32_t)root, r1 = (uint32_t)(root >> 32);
-    const uint32_t c0 = (uint32_t)((r0 >> 16) * range <= num) + (uint32_t)((r1 & 0xFFFFu) * range <= num) +
-                        (uint32_t)((r1 >> 16) * range <= num);
+    const uint32_t c0 = 3u - (above((r0 >> 16) * nr + num) + above((r1 & 0xFFFFu) * nr + num) +
+                              above((r1 >> 16) * nr + num));
     uint64_t *const p1 = nodes + c0 * stride;
     uint64_t n1 = *p1;
     const uint32_t w0 = prmt(r0, r1, 0x3210u + 0x2222u * c0);        // slot c0 | slot c0+1 << 16
@@ -473,9 +478,9 @@ GPUAR_HD uint32_t tree_decode_early_range(uint64_t &root, uint64_t *nodes, uint3
     root += 0x0001000100010000ull << (16u * c0);
     // level 1, absolute thresholds
     const uint32_t q0 = (uint32_t)n1, q1 = (uint32_t)(n1 >> 32);
-    const uint32_t c1 = (uint32_t)((below0 + (q0 >> 16)) * range <= num) +
-                        (uint32_t)((below0 + (q1 & 0xFFFFu)) * range <= num) +
-                        (uint32_t)((below0 + (q1 >> 16)) * range <= num);
+    const uint32_t num1 = below0 * nr + num;                       // what is left of num below this node
+    const uint32_t c1 = 3u - (above((q0 >> 16) * nr + num1) + above((q1 & 0xFFFFu) * nr + num1) +
+                              above((q1 >> 16) * nr + num1));
     uint32_t idx = c0 * 4u + c1;
     uint64_t *const p2 = nodes + (4u + idx) * stride;
     uint64_t n2 = *p2;
