@@ -679,12 +679,10 @@ struct BitSource {
         return bits;
     }
     GPUAR_HD bool hungry() const { return have <= 32u; }
-    GPUAR_HD void feed_if(bool on, uint32_t be_word)  // requires have <= 32 when on: lo is empty then
+    GPUAR_HD void feed_if(bool on, uint32_t be_word)  // on == hungry(): have <= 32, lo is empty then
     {
-        const uint32_t add_hi = shr_clamp(be_word, have);
-        const uint32_t add_lo = be_word << ((32u - have) & 31u);
-        hi |= on ? add_hi : 0u;
-        lo = on ? add_lo : lo;
+        hi |= shr_clamp(be_word, have);              // have >= 33 when not hungry: the clamped shift gives 0
+        lo = on ? be_word << ((32u - have) & 31u) : lo;
         have += on ? 32u : 0u;
     }
     GPUAR_HD void feed(uint32_t be_word) { feed_if(true, be_word); }

@@ -86,7 +86,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     // per-lane ring in shared memory that cp.async keeps kAhead words ahead of the reader.
     const uint32_t *const wend = reinterpret_cast<const uint32_t *>(payload) + (readable >> 2) - 1;  // last readable word
     const uint32_t *gp = wend;      // next word to request (ring) / word held in `ahead` (register)
-    uint32_t rd = 0, wr = 0;        // ring positions: words consumed / requested
+    uint32_t rd = 0;                // ring feed: words consumed
     uint32_t ahead = 0;             // register feed: prefetched word, byte-swapped only when fed
     BitSource in;
     in.start(0, 64u);
@@ -104,8 +104,18 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
         ++gp;
         in.start(((w0 << 32) | w1) << skip, 64u - skip);           // 40..64 bits
     }
+    // ring feed: ring position p holds stream word g0[min(p, p_max)] at shared address
+    // ring_s + (p mod kRing) * 128; positions rd .. rd + kAhead - 1 are requested, so one counter
+    // and 32-bit index arithmetic do (a 64-bit pointer to bump and clamp costs four instructions more)
+    const uint32_t *const g0 = clamp_ptr(gp, wend);
+    const uint32_t p_max = (uint32_t)min((ptrdiff_t)(wend - g0), (ptrdiff_t)0x3FFFFFFF);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(&sm.ring[0][lane]);
+    auto request = [&](uint32_t p) {
+        const uint32_t dst = ring_s + ((p & (kRing - 1u)) << 7);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(g0 + min(p, p_max)) : "memory");
+    };
     if (kRingFeed) {
-        for (; wr < kAhead; ++wr, ++gp) cp_async4(&sm.ring[wr][lane], clamp_ptr(gp, wend));
+        for (uint32_t p = 0; p < kAhead; ++p) request(p);
         cp_async_commit();
         cp_async_wait<0>();
     } else {
@@ -118,14 +128,13 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
             // after it was requested, so waiting for all but the kAhead-1 newest groups makes it
             // visible.
             cp_async_wait<kAhead - 1>();
-            const uint32_t w = sm.ring[rd & (kRing - 1u)][lane];
+            uint32_t w;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(ring_s + ((rd & (kRing - 1u)) << 7)) : "memory");
             const bool h = in.hungry();
             in.feed_if(h, bswap32(w));
-            if (h) cp_async4(&sm.ring[wr & (kRing - 1u)][lane], clamp_ptr(gp, wend));
+            if (h) request(rd + kAhead);
             cp_async_commit();
             rd += h ? 1u : 0u;
-            wr += h ? 1u : 0u;
-            gp += h ? 1 : 0;
         } else if (in.hungry()) {
             in.feed(bswap32(ahead));
             ++gp;
