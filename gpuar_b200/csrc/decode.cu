@@ -14,22 +14,14 @@
 //   level 3: 64 nodes (1)
 // One branch-free descent (root in registers, then 3 dependent 8-byte shared loads) finds
 // the symbol, yields cum[s] and count[s] and applies the model update (+1 on every slot
-// right of the path) in the same pass (coder_math.h: tree_level).  Interval arithmetic and renormalisation are the closed forms of
-// common.cuh; bits come from a 64-bit reservoir fed by 32-bit loads one word ahead.
+// right of the path) in the same pass (coder_math.h: tree_level).  Interval arithmetic and
+// renormalisation are the single-normalisation step of coder_math.h (narrow_total: state =
+// lower bound and range); bits come from a 64-bit reservoir fed by 32-bit words.
 #include "common.cuh"
 #include "kernels.h"
 
 #ifndef GPUAR_DEC_UNROLL
 #define GPUAR_DEC_UNROLL 4          // steps per unrolled block of the full-round loop (tuning knob)
-#endif
-#ifndef GPUAR_DEC_EARLY_BIG
-#define GPUAR_DEC_EARLY_BIG 0       // 1: multiplicative top levels also in the throughput variant
-#endif
-#ifndef GPUAR_DEC_TOTAL_SMALL
-#define GPUAR_DEC_TOTAL_SMALL 1     // 1: single-normalisation step (narrow_total) in the latency variant
-#endif
-#ifndef GPUAR_DEC_TOTAL_BIG
-#define GPUAR_DEC_TOTAL_BIG 1       // 1: ... and in the throughput variant
 #endif
 
 namespace gpuar {
@@ -144,8 +136,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     // initializeDecoder (:582-603): the first 16 bits
     uint32_t code = in.take(16u);
     refill();
-    constexpr bool kTotal = kRingFeed ? (GPUAR_DEC_TOTAL_SMALL != 0) : (GPUAR_DEC_TOTAL_BIG != 0);
-    uint32_t L = 0, V = kTotal ? 65536u : 0u;       // V = inverted upper bound, or the range itself (kTotal)
+    uint32_t L = 0, R = 65536u;                     // narrow_total state: lower bound and range
 
     const uint32_t max_raw = __reduce_max_sync(kFull, raw);
     uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)my * packet);
@@ -155,20 +146,12 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     auto step = [&](uint32_t i, uint32_t m, uint32_t sh, uint32_t slot) {
         const uint32_t T = 256u + i;
         uint32_t lo, cnt;
-        const uint32_t range = kTotal ? V : 65536u - V - L;
-        const uint32_t s = (kRingFeed || GPUAR_DEC_EARLY_BIG)
-                               ? tree_decode_early_range(root, tree, 32u, code, L, range, T, lo, cnt)
-                               : tree_decode(root, tree, 32u, unscale_range(code, L, range, T), T, lo, cnt);
+        const uint32_t s = kRingFeed ? tree_decode_early_range(root, tree, 32u, code, L, R, T, lo, cnt)
+                                     : tree_decode(root, tree, 32u, unscale_range(code, L, R, T), T, lo, cnt);
         packed |= s << (8u * slot);
-        if (kTotal) {
-            uint32_t L1, S1, t, As;
-            narrow_total(L, V, lo, lo + cnt, m, sh, L1, S1, t, As);
-            code = advance_code_total(code, t, As, in);
-        } else {
-            uint32_t k, u, U1;
-            narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
-            code = advance_code(code, k, u, in);
-        }
+        uint32_t L1, S1, t, As;
+        narrow_total(L, R, lo, lo + cnt, m, sh, L1, S1, t, As);
+        code = advance_code_total(code, t, As, in);
         refill();
     };
 

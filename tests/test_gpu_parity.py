@@ -95,6 +95,23 @@ def test_both_encode_kernels_are_bit_exact(dev, path):
         _lib.set_option(_lib.OPT_ENCODE_PATH, _lib.ENCODE_AUTO)
 
 
+def test_encode_kernels_agree_beyond_one_wave(dev):
+    """The warp-specialised kernel also serves inputs of up to two resident waves of its CTAs (three per SM);
+    125 MiB puts CTAs into a second wave.  The lane=packet kernel (oracle-checked above) is the yardstick."""
+    from gpuar_b200 import _lib
+    n = 8192 * 16000 + 123
+    x = D.mixed_device(11, 126 << 20, 0)[:n]
+    got = {}
+    try:
+        for name, path in (("fused", _lib.ENCODE_FUSED), ("ws", _lib.ENCODE_WS), ("auto", _lib.ENCODE_AUTO)):
+            _lib.set_option(_lib.OPT_ENCODE_PATH, path)
+            got[name] = dev.encode_bytes(x)
+    finally:
+        _lib.set_option(_lib.OPT_ENCODE_PATH, _lib.ENCODE_AUTO)
+    assert torch.equal(got["fused"], got["ws"]) and torch.equal(got["fused"], got["auto"])
+    assert torch.equal(dev.decode_bytes(got["ws"]), x)
+
+
 @pytest.mark.parametrize("path", ["fused", "ws"])
 @pytest.mark.parametrize("packet", [4096, 8192, 12288, 16112])
 def test_packet_size_sweep_equals_rebuilt_reference(dev, packet, path):
