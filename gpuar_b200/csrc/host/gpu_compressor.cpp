@@ -6,12 +6,25 @@
 #include "gpu_compressor.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 
 #include "../../../include/gpuar_b200.h"
 
 namespace gip {
+
+// GPUAR_B200_TRACE=1: start-up costs (context creation, page-locking) on stderr; they are in
+// neither "Compute time" nor "I/O time" (the reference does not count its cudaMallocHost either)
+static void trace(const char *what, std::chrono::steady_clock::time_point since)
+{
+    static const bool on = std::getenv("GPUAR_B200_TRACE") != nullptr;
+    if (on)
+        std::fprintf(stderr, "[gpuar] %s: %.1f ms\n", what,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - since).count());
+}
 
 static void check(int rc, const char *what)
 {
@@ -20,7 +33,9 @@ static void check(int rc, const char *what)
 
 GpuCompressor::GpuCompressor(std::size_t segmentBytes) : segmentBytes_(std::max<std::size_t>(kPacketBytes, segmentBytes / kPacketBytes * kPacketBytes))
 {
+    const auto t0 = std::chrono::steady_clock::now();
     check(gpuar_b200_init(), "gpuar_b200_init");                // replaces initConstantRange(), gpu_compressor.cpp:19
+    trace("context + constants", t0);
 }
 
 GpuCompressor::~GpuCompressor()
@@ -35,26 +50,45 @@ void GpuCompressor::chooseDevice(int id)
 {
     check(gpuar_b200_set_device(id), "gpuar_b200_set_device");
     check(gpuar_b200_init(), "gpuar_b200_init");
+    device_ = id;
 }
 
 void GpuCompressor::reserve(std::size_t inBytes, std::size_t outBytes)
 {
-    if (inBytes > inCap_) {
-        for (int b = 0; b < 2; ++b) {
-            if (in_[b]) gpuar_b200_host_free(in_[b]);
-            in_[b] = nullptr;
-            check(gpuar_b200_host_alloc(inBytes, (void **)&in_[b]), "gpuar_b200_host_alloc");
-        }
-        inCap_ = inBytes;
+    // Page-locking is the expensive part of start-up (the kernel faults in and pins every page,
+    // ~0.7 s per GiB on the B200 hosts), and the four buffers pin independently: one helper
+    // thread each.  A helper selects the device first so that it does not create a context on
+    // device 0.
+    const auto t0 = std::chrono::steady_clock::now();
+    std::uint8_t **slot[4] = {&in_[0], &in_[1], &out_[0], &out_[1]};
+    const std::size_t want[4] = {inBytes > inCap_ ? inBytes : 0, inBytes > inCap_ ? inBytes : 0,
+                                 outBytes > outCap_ ? outBytes : 0, outBytes > outCap_ ? outBytes : 0};
+    std::future<int> pinned[4];
+    const int device = device_;
+    for (int k = 0; k < 4; ++k) {
+        if (!want[k]) continue;
+        if (*slot[k]) gpuar_b200_host_free(*slot[k]);
+        *slot[k] = nullptr;
+        std::uint8_t **dst = slot[k];
+        const std::size_t bytes = want[k];
+        pinned[k] = std::async(std::launch::async, [dst, bytes, device] {
+            if (device >= 0) {
+                const int rc = gpuar_b200_set_device(device);
+                if (rc) return rc;
+            }
+            return gpuar_b200_host_alloc(bytes, (void **)dst);
+        });
     }
-    if (outBytes > outCap_) {
-        for (int b = 0; b < 2; ++b) {
-            if (out_[b]) gpuar_b200_host_free(out_[b]);
-            out_[b] = nullptr;
-            check(gpuar_b200_host_alloc(outBytes, (void **)&out_[b]), "gpuar_b200_host_alloc");
+    int rc = 0;
+    for (int k = 0; k < 4; ++k)
+        if (pinned[k].valid()) {
+            const int r = pinned[k].get();
+            if (r && !rc) rc = r;
         }
-        outCap_ = outBytes;
-    }
+    if (want[0]) inCap_ = rc ? 0 : inBytes;
+    if (want[2]) outCap_ = rc ? 0 : outBytes;
+    check(rc, "gpuar_b200_host_alloc");
+    trace("page-locked staging", t0);
 }
 
 CompressionInfo GpuCompressor::compress(ProgressMonitor *monitor)
@@ -139,8 +173,18 @@ CompressionInfo GpuCompressor::decompress(ProgressMonitor *monitor)
 
     // Segments of whole packets: the host only hops over compLen fields to find where to cut
     // (one u16 per packet); the packets themselves are indexed and decoded on the device.
-    const std::size_t segPayload = segmentBytes_ + segmentBytes_ / 16;
-    reserve(kFileHeader + segPayload + kSlotBytes + 64, segmentBytes_ + 4 * kPacketBytes);
+    // The staging is page-locked and pinning costs ~1 s per GiB: size it for this file, not for
+    // the largest segment.  The announced raw size only bounds the segment (a header that lies just
+    // means more or fewer library calls), and never below the payload size: arithmetic coding with
+    // this model expands by at most 6 %, so a file whose header says less than that is lying.
+    const std::uint64_t payloadBytes = fileBytes - kFileHeader;
+    std::uint64_t hint = 0;
+    if (gpuar_b200_gip_raw_size(header, (std::size_t)fileBytes, &hint) != 0) hint = announced;
+    hint = std::max<std::uint64_t>(std::max(hint, payloadBytes), kPacketBytes);
+    const std::size_t segRaw = (std::size_t)std::min<std::uint64_t>(
+        segmentBytes_, (hint + kPacketBytes - 1) / kPacketBytes * kPacketBytes);
+    const std::size_t segPayload = (std::size_t)std::min<std::uint64_t>(segRaw + segRaw / 16, payloadBytes + kSlotBytes);
+    reserve(kFileHeader + segPayload + kSlotBytes + 64, segRaw + 4 * kPacketBytes);
     // window [begin, end) of the staging buffer holds payload bytes not yet decoded
     std::size_t begin = 0, end = 0;
     std::uint64_t remaining = fileBytes - kFileHeader;
@@ -166,7 +210,7 @@ CompressionInfo GpuCompressor::decompress(ProgressMonitor *monitor)
             const std::size_t len = (std::size_t)pay[cut] | ((std::size_t)pay[cut + 1] << 8);
             const std::size_t r = (std::size_t)pay[cut + 2] | ((std::size_t)pay[cut + 3] << 8);
             if (len <= 4 || r > kPacketBytes) throw std::runtime_error("Incorrect file format");
-            if (cut + len > end || raw + r > segmentBytes_ + kPacketBytes) break;
+            if (cut + len > end || raw + r > segRaw + kPacketBytes) break;
             cut += len;
             raw += r;
         }

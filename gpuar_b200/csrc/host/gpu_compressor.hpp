@@ -12,11 +12,12 @@ class GpuCompressor : public Compressor {
     std::uint8_t *out_[2] = {nullptr, nullptr};
     std::size_t inCap_ = 0, outCap_ = 0;
     std::size_t segmentBytes_;         // raw bytes handled per library call (multiple of 8192)
+    int device_ = -1;                  // chooseDevice() argument; -1 = the process default (device 0)
 
     void reserve(std::size_t inBytes, std::size_t outBytes);
 
   public:
-    explicit GpuCompressor(std::size_t segmentBytes = (std::size_t)1 << 30);
+    explicit GpuCompressor(std::size_t segmentBytes = (std::size_t)128 << 20);
     ~GpuCompressor() override;
     void chooseDevice(int id);                                  // gpu_compressor.cpp:67-82, but really selects it
     CompressionInfo compress(ProgressMonitor *monitor) override;

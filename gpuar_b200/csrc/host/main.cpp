@@ -29,7 +29,7 @@ void usage()
                  "--help          print this help message\n"
                  "--host          run the codec on the host CPU (single thread), otherwise on the CUDA device\n"
                  "--device=N      CUDA device to use (default 0)\n"
-                 "--segment=MiB   raw bytes handed to the device per call (default 1024)\n"
+                 "--segment=MiB   raw bytes handed to the device per call (default 128)\n"
                  "--nointeractive accepted for compatibility\n";
 }
 
@@ -68,7 +68,7 @@ int main(int argc, char **argv)
         option(argc, argv, "out", outName);
         int device = 0;
         if (option(argc, argv, "device", value)) device = std::atoi(value.c_str());
-        std::size_t segment = (std::size_t)1 << 30;
+        std::size_t segment = (std::size_t)128 << 20;
         if (option(argc, argv, "segment", value)) segment = (std::size_t)std::atoll(value.c_str()) << 20;
 
         std::unique_ptr<Compressor> compressor;

@@ -90,3 +90,22 @@ def test_gpu_mode_files_equal_reference(tmp_path, segment_mib):
     # and the CPU mode reads what the GPU mode wrote
     assert run("d", "--host", "--in", gip, "--out", back).returncode == 0
     assert np.array_equal(np.fromfile(back, np.uint8), data)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("announced", [None, 0, 8192, 0xFFFFFFFF])
+def test_gpu_mode_decode_sizes_its_staging_without_trusting_the_header(tmp_path, announced):
+    """GpuCompressor::decompress sizes its page-locked staging from the announced raw size; the field
+    is 32 bits in the reference (file_header.hpp:61-66) and wraps for big files, so a wrong value
+    may only change how the stream is cut into segments, never the result."""
+    data = D.and3(5, (3 << 20) + 100)                               # payload ~0.56 of the raw size
+    g = O.gip_file(data)
+    for k in O.HEADER_MASKED:
+        g[k] = 0xA5
+    if announced is not None:
+        g[4:8] = np.frombuffer(int(announced).to_bytes(4, "little"), np.uint8)
+    gip, back = str(tmp_path / "in.gip"), str(tmp_path / "back.dat")
+    g.tofile(gip)
+    r = run("d", "--in", gip, "--out", back)
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(np.fromfile(back, np.uint8), data)

@@ -15,7 +15,8 @@ D.uniform(0x64, 64 << 20).tofile("$d/random_64m.dat")
 D.and3(2, 1 << 30).tofile("$d/and3_1g.dat")
 PY
 out=gpurun_out/${tag}_cli_timing.txt
-: > $out
+echo "GPUs visible: $(nvidia-smi -L | wc -l); host threads: $(nproc)" > $out
+export GPUAR_B200_TRACE=1       # start-up costs (context, page-locking) on stderr
 run() {
   echo "\$ gpuar $*" >> $out
   local t0=$(date +%s%N)
