@@ -42,6 +42,8 @@ SIGNATURES = {
     "gpuar_b200_encode": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
     "gpuar_b200_index": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _vp, _sz, _vp]),
     "gpuar_b200_decode": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _sz, _vp]),
+    "gpuar_b200_decode_packed_scratch_bytes": (_sz, [_sz, _sz]),
+    "gpuar_b200_decode_packed": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _sz, _vp]),
     "gpuar_b200_payload_bound_ex": (_sz, [_sz, _sz]),
     "gpuar_b200_encode_scratch_bytes_ex": (_sz, [_sz, _sz]),
     "gpuar_b200_encode_ex": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),

@@ -56,6 +56,7 @@ class DeviceCodec:
         init(self.device)
         self._scratch = None
         self._iscratch = None
+        self._pscratch = None
 
     def _buf(self, attr: str, nbytes: int) -> torch.Tensor:
         cur = getattr(self, attr)
@@ -90,7 +91,7 @@ class DeviceCodec:
               result: torch.Tensor | None = None, packet: int = PACKET):
         """Packet offsets of payload[:c] (payload readable PAD bytes past c).
 
-        Returns (offsets int64[max_packets], result int64[4] = packets, raw bytes, status, candidates)."""
+        Returns (offsets int64[max_packets], result int64[4] = packets, raw bytes, status, ragged flag)."""
         assert payload.is_cuda and payload.dtype == torch.uint8 and payload.numel() >= c + PAD
         if offsets is None:
             offsets = torch.empty(max(1, max_packets), dtype=torch.int64, device=payload.device)
@@ -114,6 +115,19 @@ class DeviceCodec:
                                              out.data_ptr(), out.numel(), _stream()), "gpuar_b200_decode_ex")
         return out
 
+    def decode_packed(self, payload: torch.Tensor, c: int, offsets: torch.Tensor, n_packets: int,
+                      out: torch.Tensor, packet: int = PACKET) -> torch.Tensor:
+        """Decode n_packets packets back to back into `out` (short packets allowed anywhere, as in
+        the reference's CPU decoder).  Returns total[1] int64 on device = raw bytes of the packets;
+        packets that would end past out.numel() are not written."""
+        total = torch.zeros(1, dtype=torch.int64, device=payload.device)
+        scratch = self._buf("_pscratch", int(lib().gpuar_b200_decode_packed_scratch_bytes(n_packets, packet)))
+        with torch.cuda.device(self.device):
+            check(lib().gpuar_b200_decode_packed(payload.data_ptr(), c, packet, offsets.data_ptr(), n_packets,
+                                                 out.data_ptr(), out.numel(), total.data_ptr(), scratch.data_ptr(),
+                                                 scratch.numel(), _stream()), "gpuar_b200_decode_packed")
+        return total
+
     # -------------------------------------------------- convenience (synchronises)
     def encode_bytes(self, x: torch.Tensor, packet: int = PACKET) -> torch.Tensor:
         payload, total, _ = self.encode(x, packet=packet)
@@ -126,9 +140,14 @@ class DeviceCodec:
         padded[:c] = payload
         max_packets = c // 5 + 1
         offsets, result = self.index(padded, c, max_packets, packet=packet)
-        packets, raw, status, _ = (int(v) for v in result.tolist())
+        packets, raw, status, ragged = (int(v) for v in result.tolist())
         if status != 0:
             raise GpuarError(status, "gpuar_b200_index")
+        if ragged:                                                  # short packets before the last one
+            out = torch.empty(raw + 16, dtype=torch.uint8, device=payload.device)
+            total = self.decode_packed(padded, c, offsets, packets, out, packet=packet)
+            assert int(total.item()) == raw
+            return out[:raw]
         out = self.decode(padded, c, offsets, packets, packet=packet)
         return out[:raw]
 

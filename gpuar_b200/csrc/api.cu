@@ -273,6 +273,56 @@ int gpuar_b200_decode(const uint8_t *d_payload, size_t c, const uint64_t *d_offs
     return gpuar_b200_decode_ex(d_payload, c, kPacket, d_offsets, n_packets, d_out, out_cap, stream);
 }
 
+/* packed decode scratch: [strided output: packets*packet][sizes: packets*4][descriptors] */
+struct PackedPlan {
+    size_t off_strided, off_sizes, off_desc, total;
+};
+static PackedPlan packed_plan(size_t packets, size_t packet)
+{
+    PackedPlan p{};
+    size_t o = 0;
+    p.off_strided = o;
+    o += align_up(packets * packet + 64, 256);
+    p.off_sizes = o;
+    o += align_up(packets * 4 + 4, 256);
+    p.off_desc = o;
+    o += align_up(compact_desc_bytes(packets), 256);
+    p.total = o;
+    return p;
+}
+
+size_t gpuar_b200_decode_packed_scratch_bytes(size_t n_packets, size_t packet_bytes)
+{
+    return packet_ok(packet_bytes) ? packed_plan(n_packets, packet_bytes).total : 0;
+}
+
+int gpuar_b200_decode_packed(const uint8_t *d_payload, size_t c, size_t packet_bytes, const uint64_t *d_offsets,
+                             size_t n_packets, uint8_t *d_out, size_t out_cap, uint64_t *d_out_bytes, void *d_scratch,
+                             size_t scratch_bytes, void *stream)
+{
+    if (!packet_ok(packet_bytes) || !d_out_bytes) return GPUAR_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!n_packets) return ck(cudaMemsetAsync(d_out_bytes, 0, sizeof(uint64_t), st));
+    if (!d_payload || !d_offsets || !d_out || !d_scratch) return GPUAR_E_ARG;
+    if (((uintptr_t)d_payload | (uintptr_t)d_out | (uintptr_t)d_scratch) & 15u) return GPUAR_E_ARG;
+    const PackedPlan p = packed_plan(n_packets, packet_bytes);
+    if (n_packets > 0xFFFFFFF0ull || scratch_bytes < p.total) return GPUAR_E_ARG;
+    uint8_t *s = static_cast<uint8_t *>(d_scratch);
+    uint32_t *sizes = reinterpret_cast<uint32_t *>(s + p.off_sizes);
+    cudaError_t e;
+    {
+        Scope t(GPUAR_SPAN_DECODE, st);
+        e = launch_decode(d_payload, c + GPUAR_PAD_BYTES, d_offsets, 0, (uint32_t)n_packets, s + p.off_strided,
+                          (uint32_t)packet_bytes, st);
+    }
+    if (e != cudaSuccess) return ck(e);
+    Scope t(GPUAR_SPAN_COMPACT, st);
+    e = launch_raw_sizes(d_payload, c, d_offsets, (uint32_t)n_packets, (uint32_t)packet_bytes, sizes, st);
+    if (e != cudaSuccess) return ck(e);
+    return ck(launch_compact(s + p.off_strided, (uint32_t)packet_bytes, sizes, (uint32_t)n_packets, d_out,
+                             reinterpret_cast<uint64_t *>(s + p.off_desc), d_out_bytes, st, (uint64_t)out_cap));
+}
+
 /* ------------------------------------------------------------------- options */
 int gpuar_b200_set_option(int key, long long value)
 {
@@ -442,31 +492,67 @@ int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *ou
     if (chunk_bytes < ((size_t)2 << 20)) chunk_bytes = (size_t)2 << 20;
     if (chunk_bytes > ((size_t)256 << 20)) chunk_bytes = (size_t)256 << 20;
 
-    const size_t max_packets = out_cap / kPacket + 2;
-    if (h->h_offsets_cap < max_packets) {
-        if (h->h_offsets) cudaFreeHost(h->h_offsets);
-        h->h_offsets = nullptr;
-        h->h_offsets_cap = 0;
-        if ((e = cudaMallocHost(&h->h_offsets, max_packets * sizeof(uint64_t))) != cudaSuccess) return ck(e);
-        h->h_offsets_cap = max_packets;
-    }
-    if ((e = h->offsets.need(max_packets * sizeof(uint64_t))) != cudaSuccess) return ck(e);
-    if ((e = h->big_out.need(max_packets * (size_t)kPacket)) != cudaSuccess) return ck(e);
+    // Offsets for as many packets as a stream of full packets has; a stream with short packets in
+    // it (never written by the reference) may hold more: grown on demand, below.
+    size_t max_packets = out_cap / kPacket + 2;
+    auto drain_all = [&]() -> cudaError_t {
+        cudaError_t first = cudaSuccess;
+        for (int l = 0; l < kLanes; ++l) {
+            const cudaError_t es = cudaStreamSynchronize(h->stream[l]);
+            if (first == cudaSuccess) first = es;
+        }
+        cudaError_t es = cudaStreamSynchronize(h->up);
+        if (first == cudaSuccess) first = es;
+        es = cudaStreamSynchronize(h->down);
+        return first == cudaSuccess ? es : first;
+    };
+    auto reserve_offsets = [&](size_t want, size_t keep) -> cudaError_t {
+        if (h->h_offsets_cap < want) {
+            uint64_t *fresh = nullptr;
+            cudaError_t er = cudaMallocHost(&fresh, want * sizeof(uint64_t));
+            if (er != cudaSuccess) return er;
+            if (keep) memcpy(fresh, h->h_offsets, keep * sizeof(uint64_t));
+            if (h->h_offsets) cudaFreeHost(h->h_offsets);
+            h->h_offsets = fresh;
+            h->h_offsets_cap = want;
+        }
+        return h->offsets.need(want * sizeof(uint64_t));
+    };
+    if ((e = reserve_offsets(max_packets, 0)) != cudaSuccess) return ck(e);
+    // device mirror of the output: chunk k lands at its raw offset rounded up to 16 bytes
+    const size_t chunks_bound = c / chunk_bytes + 2;
+    if ((e = h->big_out.need(out_cap + 16 * chunks_bound + kPacket + 64)) != cudaSuccess) return ck(e);
     if ((e = cudaMemsetAsync(d_pay + c, 0, GPUAR_PAD_BYTES, h->stream[0])) != cudaSuccess) return ck(e);
     if ((e = cudaEventRecord(h->ready, h->stream[0])) != cudaSuccess) return ck(e);
+    // a chunk of full packets holds at most chunk_bytes / 210 of them (8192 equal bytes code into
+    // 210); the bound only cuts chunks of short packets, whose scratch is sized by the packet count
+    const size_t chunk_packets = chunk_bytes / 128 + 1024;
 
-    size_t pos = 0, packets = 0, total = 0, lane = 0;
+    size_t pos = 0, packets = 0, total = 0, lane = 0, dev_pos = 0;
     int status = 0;
     while (pos < c && status == 0) {
         // one chunk: whole packets until chunk_bytes of payload
-        const size_t p0 = packets, a = pos;
-        while (pos < c && pos - a < chunk_bytes) {
+        const size_t p0 = packets, a = pos, raw0 = total;
+        const size_t dev0 = dev_pos;
+        bool ragged = false;                                             // a short packet that is not the chunk's last
+        size_t last_raw = kPacket;
+        while (pos < c && pos - a < chunk_bytes && packets - p0 < chunk_packets) {
             if (c - pos < kHdr) { status = GPUAR_E_FORMAT; break; }
             const size_t len = (size_t)pay[pos] | ((size_t)pay[pos + 1] << 8);
             const size_t r = (size_t)pay[pos + 2] | ((size_t)pay[pos + 3] << 8);
             if (len <= kHdr || len > c - pos) { status = GPUAR_E_FORMAT; break; }
-            if (r == 0 || r > kPacket || (r != kPacket && pos + len != c)) { status = GPUAR_E_UNSUPPORTED; break; }
-            if (packets >= max_packets || total + r > out_cap || !out) { status = GPUAR_E_ARG; break; }
+            if (r == 0 || r > kPacket) { status = GPUAR_E_UNSUPPORTED; break; }
+            if (total + r > out_cap || !out) { status = GPUAR_E_ARG; break; }
+            if (packets >= max_packets) {
+                // more packets than full ones would make: wait for the chunks in flight (they read
+                // the offset arrays), then double the arrays
+                e = drain_all();
+                if (e == cudaSuccess) e = reserve_offsets(max_packets * 2, packets);
+                if (e != cudaSuccess) return ck(e);
+                max_packets *= 2;
+            }
+            ragged = ragged || last_raw != kPacket;
+            last_raw = r;
             h->h_offsets[packets++] = pos;
             total += r;
             pos += len;
@@ -488,23 +574,26 @@ int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *ou
         if (e == cudaSuccess) e = cudaEventRecord(h->arrived[l], h->up);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->arrived[l], 0);
         if (e != cudaSuccess) return ck(e);
-        uint8_t *d_out = (uint8_t *)h->big_out.p + p0 * kPacket;
-        rc = gpuar_b200_decode(d_pay, c, d_off, m, d_out, m * (size_t)kPacket, st);
+        uint8_t *d_out = (uint8_t *)h->big_out.p + dev0;
+        dev_pos = align_up(dev0 + (total - raw0), 16);
+        if (!ragged) {
+            rc = gpuar_b200_decode(d_pay, c, d_off, m, d_out, m * (size_t)kPacket, st);
+        } else {
+            // short packets inside the chunk (never written by the reference, legal for its CPU
+            // decoder): decode at the 8192-byte stride into the lane's scratch, then close the gaps
+            e = h->scratch[l].need(gpuar_b200_decode_packed_scratch_bytes(m, kPacket));
+            if (e != cudaSuccess) return ck(e);
+            rc = gpuar_b200_decode_packed(d_pay, c, kPacket, d_off, m, d_out, total - raw0, &h->h_total[l],
+                                          h->scratch[l].p, h->scratch[l].cap, st);
+        }
         if (rc) return rc;
-        const size_t lo = p0 * kPacket, hi = (lo + m * kPacket < total) ? lo + m * kPacket : total;
         e = cudaEventRecord(h->done[l], st);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(h->down, h->done[l], 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out + lo, d_out, hi - lo, cudaMemcpyDeviceToHost, h->down);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out + raw0, d_out, total - raw0, cudaMemcpyDeviceToHost, h->down);
         if (e != cudaSuccess) return ck(e);
     }
-    for (int l = 0; l < kLanes; ++l) {
-        cudaError_t es = cudaStreamSynchronize(h->stream[l]);
-        if (e == cudaSuccess) e = es;
-    }
     {
-        cudaError_t es = cudaStreamSynchronize(h->up);
-        if (e == cudaSuccess) e = es;
-        es = cudaStreamSynchronize(h->down);
+        const cudaError_t es = drain_all();
         if (e == cudaSuccess) e = es;
     }
     if (status) return status;

@@ -220,10 +220,14 @@ __device__ __forceinline__ void warp_copy_any(uint8_t *__restrict__ dst, const u
     }
 }
 
+// kGuard: the destination holds `cap` bytes and the sizes come from an untrusted stream (the
+// rawLen fields of a foreign .gip, decode side): a packet that would end past `cap` is not
+// copied; *total_out still reports the full sum, so the caller sees that it did not fit.
+template <bool kGuard>
 __global__ void __launch_bounds__(kCompactThreads)
 compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const uint32_t *__restrict__ sizes,
                uint32_t n_packets, uint32_t tile_packets, uint8_t *__restrict__ payload, uint64_t *__restrict__ desc,
-               uint32_t *__restrict__ ticket, uint64_t *__restrict__ total_out)
+               uint32_t *__restrict__ ticket, uint64_t *__restrict__ total_out, uint64_t cap)
 {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_off[kMaxTilePackets + 1];
@@ -270,6 +274,7 @@ compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const ui
 
     const uint64_t base = s_base;
     for (uint32_t q = warp; q < count; q += kCompactThreads / 32u) {
+        if (kGuard && base + s_off[q + 1u] > cap) continue;
         warp_copy_unaligned(payload + base + s_off[q], slots + (size_t)(first + q) * slot_stride,
                             s_off[q + 1u] - s_off[q], lane);
     }
@@ -370,7 +375,7 @@ size_t compact_desc_bytes(size_t packets)
 
 cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const uint32_t *d_sizes,
                            uint32_t packets, uint8_t *d_payload, uint64_t *d_desc, uint64_t *d_total,
-                           cudaStream_t st)
+                           cudaStream_t st, uint64_t cap)
 {
     const uint32_t tile = compact_tile_for(packets);
     const uint32_t tiles = (packets + tile - 1) / tile;
@@ -378,8 +383,12 @@ cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const u
     if (e != cudaSuccess) return e;
     if (!packets) return cudaMemsetAsync(d_total, 0, sizeof(uint64_t), st);
     uint32_t *ticket = reinterpret_cast<uint32_t *>(d_desc + tiles);
-    compact_kernel<<<tiles, kCompactThreads, 0, st>>>(d_slots, slot_stride, d_sizes, packets, tile, d_payload,
-                                                      d_desc, ticket, d_total);
+    if (cap == kNoCap)
+        compact_kernel<false><<<tiles, kCompactThreads, 0, st>>>(d_slots, slot_stride, d_sizes, packets, tile,
+                                                                 d_payload, d_desc, ticket, d_total, cap);
+    else
+        compact_kernel<true><<<tiles, kCompactThreads, 0, st>>>(d_slots, slot_stride, d_sizes, packets, tile,
+                                                                d_payload, d_desc, ticket, d_total, cap);
     count_launch();
     return cudaGetLastError();
 }

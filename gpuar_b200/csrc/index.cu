@@ -20,7 +20,8 @@
 //   6. rank   thread r walks the tables along the base-32 digits of r: offsets[r].
 //
 // If the fast path cannot be used (too many candidates for the scratch, chain not
-// reaching C) step 5 falls back to a serial walk, which also validates the stream.
+// reaching C through full packets) step 5 falls back to a serial walk, which also validates
+// the stream and accepts short packets anywhere (flagged in result[3]).
 #include "common.cuh"
 #include "kernels.h"
 #include "lookback.cuh"
@@ -260,19 +261,23 @@ __global__ void index_finish_kernel(const uint8_t *__restrict__ payload, size_t 
             result[0] = packets;
             result[1] = (packets - 1u) * packet + last_raw;
             result[2] = packets <= max_packets ? 0ull : (uint64_t)(int64_t)-1;   // GPUAR_E_ARG
-            result[3] = n;
+            result[3] = 0;                                          // every packet but the last is full
             return;
         }
     }
-    // serial fallback: walk and validate (cpu_compressor.cpp:47-78)
+    // serial fallback: walk and validate (cpu_compressor.cpp:47-78).  This is also the path of
+    // streams with short packets before the last one (what the reference's CPU decoder accepts,
+    // cpu_compressor.cpp:60-70, and its GPU decoder does not, gpuar_kernel.cu:924): they are
+    // indexed here and flagged in result[3]; gpuar_b200_decode_packed writes them.
     ctl->serial = 1;
-    uint64_t o = 0, k = 0, raw_total = 0;
+    uint64_t o = 0, k = 0, raw_total = 0, ragged = 0;
     int64_t status = 0;
     while (o < c) {
         if (c - o < kHdr) { status = -2; break; }
         const uint64_t len = ld16(payload + o), raw = ld16(payload + o + 2);
         if (len <= kHdr || len > c - o) { status = -2; break; }
-        if (raw == 0 || raw > packet || (raw != packet && o + len != c)) { status = -4; break; }
+        if (raw == 0 || raw > packet) { status = -4; break; }
+        if (raw != packet && o + len != c) ragged = 1;
         if (k < max_packets) offsets[k] = o; else status = -1;
         ++k;
         raw_total += raw;
@@ -281,7 +286,7 @@ __global__ void index_finish_kernel(const uint8_t *__restrict__ payload, size_t 
     result[0] = k;
     result[1] = raw_total;
     result[2] = (uint64_t)status;
-    result[3] = n;
+    result[3] = ragged;
 }
 
 // ---- 6. rank
@@ -302,6 +307,26 @@ index_rank_kernel(const uint64_t *__restrict__ cand, uint32_t cap, const IndexCt
         for (uint32_t h = 0; h < digit; ++h) pos = S[pos];
     }
     offsets[r] = cand[pos];
+}
+
+// ---- raw sizes of indexed packets (for the packed output layout of ragged streams)
+__global__ void __launch_bounds__(256)
+raw_sizes_kernel(const uint8_t *__restrict__ payload, size_t c, const uint64_t *__restrict__ offsets,
+                 uint32_t n_packets, uint32_t packet, uint32_t *__restrict__ sizes)
+{
+    const uint32_t p = blockIdx.x * 256u + threadIdx.x;
+    if (p >= n_packets) return;
+    const uint64_t o = offsets[p];
+    sizes[p] = o + kHdr <= c ? min(ld16(payload + o + 2), packet) : 0u;    // exactly what decode_kernel writes
+}
+
+cudaError_t launch_raw_sizes(const uint8_t *d_payload, size_t c, const uint64_t *d_offsets, uint32_t packets,
+                             uint32_t packet, uint32_t *d_sizes, cudaStream_t st)
+{
+    if (!packets) return cudaSuccess;
+    raw_sizes_kernel<<<(packets + 255u) / 256u, 256, 0, st>>>(d_payload, c, d_offsets, packets, packet, d_sizes);
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets, size_t max_packets,

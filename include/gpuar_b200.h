@@ -78,7 +78,9 @@ int gpuar_b200_encode(const uint8_t *d_in, size_t n, uint8_t *d_payload, size_t 
  *   d_payload     16-byte aligned, c payload bytes, readable to c + GPUAR_PAD_BYTES.
  *   d_offsets     device u64[max_packets]: byte offset of each packet in d_payload.
  *   d_result      device u64[4]: [0] packet count, [1] total rawLen, [2] status
- *                 (0 ok, else a GPUAR_E_* code as two's complement), [3] reserved.
+ *                 (0 ok, else a GPUAR_E_* code as two's complement), [3] 1 if a packet other
+ *                 than the last is short (rawLen < 8192; never written by the reference, but
+ *                 legal for its CPU decoder): decode such a stream with gpuar_b200_decode_packed.
  * max_packets >= c/5 + 1 is always enough; >= ceil(raw/8192) suffices for well-formed input.
  */
 int gpuar_b200_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets, size_t max_packets,
@@ -86,11 +88,26 @@ int gpuar_b200_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets, si
 
 /* ---------------------------------------------------------------- decode
  * Packets at d_offsets[0..n_packets) -> d_out; packet p is written at p * 8192
- * (gpuar_kernel.cu:924).  Replaces garDecompressExecutor (gpuar.h:78).
+ * (gpuar_kernel.cu:924), rawLen bytes of it.  Replaces garDecompressExecutor (gpuar.h:78).
  *   d_out  16-byte aligned, capacity >= n_packets * 8192.
  */
 int gpuar_b200_decode(const uint8_t *d_payload, size_t c, const uint64_t *d_offsets, size_t n_packets,
                       uint8_t *d_out, size_t out_cap, void *stream);
+
+/* ----------------------------------------------------- decode, packed output
+ * The same packets written back to back: packet p lands at the sum of the rawLen fields of the
+ * packets before it.  This is the layout of the reference's CPU decoder (cpu_compressor.cpp:60-70:
+ * fwrite of rawLen bytes per packet), which -- unlike its GPU decoder -- accepts short packets
+ * anywhere in the stream; gpuar_b200_index flags such streams in d_result[3].  For streams whose
+ * packets are all full except the last, it equals gpuar_b200_decode (which is one kernel cheaper).
+ *   d_out        16-byte aligned, out_cap bytes; packets that would end past out_cap are not written.
+ *   d_out_bytes  device u64: total raw bytes of the n_packets packets (compare with out_cap).
+ *   d_scratch    16-byte aligned, gpuar_b200_decode_packed_scratch_bytes(n_packets, packet_bytes).
+ */
+size_t gpuar_b200_decode_packed_scratch_bytes(size_t n_packets, size_t packet_bytes);
+int gpuar_b200_decode_packed(const uint8_t *d_payload, size_t c, size_t packet_bytes, const uint64_t *d_offsets,
+                             size_t n_packets, uint8_t *d_out, size_t out_cap, uint64_t *d_out_bytes, void *d_scratch,
+                             size_t scratch_bytes, void *stream);
 
 /* ------------------------------------------------ other packet sizes (config sweep)
  * The packet size is a compile-time constant of the reference (gpu.h:12-13) and is not recorded

@@ -27,13 +27,13 @@ run() {
 # config 1: the reference's CPU-runnable case (single host thread)
 run c --host --in=$d/random_64m.dat --out=$d/host.gip
 run d --host --in=$d/host.gip --out=$d/host.out
-# config 2: the same file on the device (first call pays CUDA context creation; the second shows the steady state)
-run c --in=$d/random_64m.dat --out=$d/dev.gip
-run c --in=$d/random_64m.dat --out=$d/dev.gip
-run d --in=$d/dev.gip --out=$d/dev.out
+# config 2: the same file on the device.  A fresh box pages the driver and the binaries in during the
+# first GPU processes, so every device command runs four times; the last three are the steady state.
+for rep in 1 2 3 4; do run c --in=$d/random_64m.dat --out=$d/dev.gip; done
+for rep in 1 2 3 4; do run d --in=$d/dev.gip --out=$d/dev.out; done
 # config 3 through the files
-run c --in=$d/and3_1g.dat --out=$d/and3.gip
-run d --in=$d/and3.gip --out=$d/and3.out
+for rep in 1 2 3; do run c --in=$d/and3_1g.dat --out=$d/and3.gip; done
+for rep in 1 2 3; do run d --in=$d/and3.gip --out=$d/and3.out; done
 {
   echo "payloads identical (bytes >= 20): $(cmp -i 20 $d/host.gip $d/dev.gip > /dev/null && echo yes || echo NO)"
   md5sum $d/random_64m.dat $d/host.out $d/dev.out | awk '{print $1}' | sort -u | wc -l | sed 's/^/distinct md5 over input, host round trip, device round trip: /'
