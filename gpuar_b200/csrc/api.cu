@@ -452,13 +452,19 @@ int gpuar_b200_compress_host(const uint8_t *in, size_t n, uint8_t *gip, size_t g
         if (e != cudaSuccess) break;
         rc = gpuar_b200_encode((const uint8_t *)h->in[l].p, m, (uint8_t *)h->pay[l].p, h->pay[l].cap,
                                &h->h_total[l], nullptr, h->scratch[l].p, h->scratch[l].cap, st);
-        if (rc) return rc;
+        if (rc) break;
         e = cudaEventRecord(h->done[l], st);
     }
-    for (size_t k = (chunks > (size_t)kLanes ? chunks - kLanes : 0); k < chunks && e == cudaSuccess; ++k)
+    for (size_t k = (chunks > (size_t)kLanes ? chunks - kLanes : 0); k < chunks && e == cudaSuccess && rc == 0; ++k)
         e = drain(k);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->down);
-    if (e != cudaSuccess) return ck(e);
+    if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(h->down);
+    if (e != cudaSuccess || rc) {
+        // errors in mid-stream: nothing may still be reading or writing the caller's buffers on return
+        for (int l = 0; l < kLanes; ++l) cudaStreamSynchronize(h->stream[l]);
+        cudaStreamSynchronize(h->up);
+        cudaStreamSynchronize(h->down);
+        return rc ? rc : ck(e);
+    }
     gpuar_b200_write_header(gip, n, pos);
     *gip_bytes = pos;
     return 0;
@@ -528,6 +534,8 @@ int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *ou
     // 210); the bound only cuts chunks of short packets, whose scratch is sized by the packet count
     const size_t chunk_packets = chunk_bytes / 128 + 1024;
 
+    // errors in mid-stream: nothing may still be reading the caller's buffers (or ours) on return
+    auto fail = [&](int code) { drain_all(); return code; };
     size_t pos = 0, packets = 0, total = 0, lane = 0, dev_pos = 0;
     int status = 0;
     while (pos < c && status == 0) {
@@ -548,7 +556,7 @@ int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *ou
                 // the offset arrays), then double the arrays
                 e = drain_all();
                 if (e == cudaSuccess) e = reserve_offsets(max_packets * 2, packets);
-                if (e != cudaSuccess) return ck(e);
+                if (e != cudaSuccess) return fail(ck(e));
                 max_packets *= 2;
             }
             ragged = ragged || last_raw != kPacket;
@@ -573,7 +581,7 @@ int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *ou
             e = cudaMemcpyAsync(d_off, h->h_offsets + p0, m * sizeof(uint64_t), cudaMemcpyHostToDevice, h->up);
         if (e == cudaSuccess) e = cudaEventRecord(h->arrived[l], h->up);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->arrived[l], 0);
-        if (e != cudaSuccess) return ck(e);
+        if (e != cudaSuccess) return fail(ck(e));
         uint8_t *d_out = (uint8_t *)h->big_out.p + dev0;
         dev_pos = align_up(dev0 + (total - raw0), 16);
         if (!ragged) {
@@ -582,15 +590,15 @@ int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *ou
             // short packets inside the chunk (never written by the reference, legal for its CPU
             // decoder): decode at the 8192-byte stride into the lane's scratch, then close the gaps
             e = h->scratch[l].need(gpuar_b200_decode_packed_scratch_bytes(m, kPacket));
-            if (e != cudaSuccess) return ck(e);
+            if (e != cudaSuccess) return fail(ck(e));
             rc = gpuar_b200_decode_packed(d_pay, c, kPacket, d_off, m, d_out, total - raw0, &h->h_total[l],
                                           h->scratch[l].p, h->scratch[l].cap, st);
         }
-        if (rc) return rc;
+        if (rc) return fail(rc);
         e = cudaEventRecord(h->done[l], st);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(h->down, h->done[l], 0);
         if (e == cudaSuccess) e = cudaMemcpyAsync(out + raw0, d_out, total - raw0, cudaMemcpyDeviceToHost, h->down);
-        if (e != cudaSuccess) return ck(e);
+        if (e != cudaSuccess) return fail(ck(e));
     }
     {
         const cudaError_t es = drain_all();
