@@ -31,7 +31,13 @@ namespace gpuar {
 
 constexpr uint32_t kRound = 32;
 constexpr uint32_t kCoderBlock = GPUAR_WS_CODER_BLOCK;
-constexpr uint32_t kWsThreads = 192;
+#ifndef GPUAR_WS_WARPS
+#define GPUAR_WS_WARPS 6            // tuning knob: warps per CTA (6 or 8; warps without a role exit at once)
+#endif
+#ifndef GPUAR_WS_ROLE_MAP
+#define GPUAR_WS_ROLE_MAP 0xFF543210u   // tuning knob: nibble w = role of warp w (0xF = none): which roles share a scheduler
+#endif
+constexpr uint32_t kWsThreads = 32u * GPUAR_WS_WARPS;
 #ifndef GPUAR_WS_SWAP_BD
 #define GPUAR_WS_SWAP_BD 0          // tuning knob: which of warps 1 / 2 takes level 2 and which the leaves
 #endif
@@ -141,7 +147,7 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
     extern __shared__ __align__(16) uint8_t ws_smem[];           // 72 KB: above the static limit
     WsShared &sm = *reinterpret_cast<WsShared *>(ws_smem);
     const uint32_t lane = lane_id();
-    const uint32_t role = threadIdx.x >> 5;
+    const uint32_t role = (GPUAR_WS_ROLE_MAP >> (4u * (threadIdx.x >> 5))) & 0xFu;
     const uint32_t my = blockIdx.x * 32u + lane;
     const bool mine = my < n_packets;
     const size_t off = (size_t)my * packet;
@@ -248,7 +254,7 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
             if (r + 2u < rounds) bar_arrive<kPairCount>(kCEmpty + b);
             bar_arrive<kPairCount>(kFFull + b);
         }
-    } else {
+    } else if (role == 4u) {
         // ------------------------------------------------------------ BITS
         uint32_t pend = 0;
         uint8_t *const slot = slots + (size_t)my * slot_stride;
