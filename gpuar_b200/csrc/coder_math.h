@@ -457,9 +457,119 @@ GPUAR_HD uint32_t tree_decode(uint64_t &root, uint64_t *nodes, uint32_t stride, 
 // level-2 node loads are issued before `target` exists; the two lower levels then run on
 // `target` as in tree_decode.  Same result, the dependent chain is ~2 shared-memory round
 // trips shorter.  (t * range <= 8448 * 65536 < 2^30, num < 2^30: 32-bit compares are exact.)
+#ifndef GPUAR_DEC_SPEC
+#define GPUAR_DEC_SPEC 7            // tuning knob: bits 0 / 1 / 2 = speculative loads for tree levels 1 / 2 / 3
+#endif
+
+// bitwise select: m = all ones picks x, m = 0 picks y (one LOP3)
+GPUAR_HD uint32_t bsel(uint32_t m, uint32_t x, uint32_t y) { return (x & m) | (y & ~m); }
+// one of four by the three "threshold above target" masks of a level (m0 implies m1 implies m2):
+// child 0 iff m0, child 1 iff m1 & ~m0, child 2 iff m2 & ~m1, child 3 iff ~m2; two selects deep
+GPUAR_HD uint32_t pick4(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    return bsel(m1, bsel(m0, a, b), bsel(m2, c, d));
+}
+
+// Variant of tree_decode_early_range whose node loads do not wait for the child index: the
+// four candidates of the next level are loaded as soon as their parent is known (level 1: at
+// the top of the step, level 2: once the level-0 child is known) and the right one is picked
+// with two bitwise selects on the sign masks of the threshold tests -- a shared-memory round
+// trip (~30 cycles) on the dependent chain becomes ~10 cycles of logic, for three more loads
+// and six selects per level.  Same result as tree_decode_early_range.
+GPUAR_HD uint32_t tree_decode_spec_range(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t code,
+                                         uint32_t L, uint32_t range, uint32_t T, uint32_t &lo, uint32_t &cnt)
+{
+    const uint32_t num = (((code - L) & 0xFFFFu) + 1u) * T - 1u;
+    const uint32_t nr = 0u - range;
+    auto mask = [](uint32_t d) { return (uint32_t)((int32_t)d >> 31); };   // all ones if the threshold lies above the target
+    // level-1 candidates: independent of everything in this step
+    const uint64_t a1 = nodes[0], b1 = nodes[stride], c1n = nodes[2u * stride], d1n = nodes[3u * stride];
+    // level 0
+    const uint32_t r0 = (uint32_t)root, r1 = (uint32_t)(root >> 32);
+    const uint32_t t0 = r0 >> 16, t1 = r1 & 0xFFFFu, t2 = r1 >> 16;
+    const uint32_t e0 = t0 * nr + num, e1 = t1 * nr + num, e2 = t2 * nr + num;     // num - threshold * range
+    const uint32_t m0 = mask(e0), m1 = mask(e1), m2 = mask(e2);
+    const uint32_t c0 = 3u + m0 + m1 + m2;
+    uint64_t *const p1 = nodes + c0 * stride;
+    const uint32_t q0 = pick4(m0, m1, m2, (uint32_t)a1, (uint32_t)b1, (uint32_t)c1n, (uint32_t)d1n);
+    const uint32_t q1 = pick4(m0, m1, m2, (uint32_t)(a1 >> 32), (uint32_t)(b1 >> 32), (uint32_t)(c1n >> 32),
+                              (uint32_t)(d1n >> 32));
+    const uint32_t num1 = pick4(m0, m1, m2, num, e0, e1, e2);       // what is left of num below the child
+    const uint32_t below0 = pick4(m0, m1, m2, 0u, t0, t1, t2);
+    const uint32_t above0 = pick4(m0, m1, m2, t0, t1, t2, T);
+    root += 0x0001000100010000ull << (16u * c0);
+    // level-2 candidates of that child
+    uint64_t *const g2 = nodes + (4u + c0 * 4u) * stride;
+    uint64_t a2 = 0, b2 = 0, c2n = 0, d2n = 0;
+    if (GPUAR_DEC_SPEC & 2) {
+        a2 = g2[0];
+        b2 = g2[stride];
+        c2n = g2[2u * stride];
+        d2n = g2[3u * stride];
+    }
+    // level 1, absolute thresholds
+    const uint32_t u0 = q0 >> 16, u1 = q1 & 0xFFFFu, u2 = q1 >> 16;
+    const uint32_t f0 = u0 * nr + num1, f1 = u1 * nr + num1, f2 = u2 * nr + num1;
+    const uint32_t k0 = mask(f0), k1 = mask(f1), k2 = mask(f2);
+    const uint32_t c1 = 3u + k0 + k1 + k2;
+    uint32_t idx = c0 * 4u + c1;
+    uint64_t *const p2 = g2 + c1 * stride;
+    uint64_t *const g3 = nodes + (20u + idx * 4u) * stride;
+    uint64_t a3 = 0, b3 = 0, c3n = 0, d3n = 0;
+    if (GPUAR_DEC_SPEC & 4) {
+        a3 = g3[0];
+        b3 = g3[stride];
+        c3n = g3[2u * stride];
+        d3n = g3[3u * stride];
+    }
+    uint64_t n2;
+    if (GPUAR_DEC_SPEC & 2) {
+        const uint32_t lo2 = pick4(k0, k1, k2, (uint32_t)a2, (uint32_t)b2, (uint32_t)c2n, (uint32_t)d2n);
+        const uint32_t hi2 = pick4(k0, k1, k2, (uint32_t)(a2 >> 32), (uint32_t)(b2 >> 32), (uint32_t)(c2n >> 32),
+                                   (uint32_t)(d2n >> 32));
+        n2 = ((uint64_t)hi2 << 32) | lo2;
+    } else {
+        n2 = *p2;
+    }
+    const uint32_t below1 = below0 + pick4(k0, k1, k2, 0u, u0, u1, u2);
+    const uint32_t above1 = pick4(k0, k1, k2, below0 + u0, below0 + u1, below0 + u2, above0);
+    *p1 = (((uint64_t)q1 << 32) | q0) + (0x0001000100010000ull << (16u * c1));
+    // levels 2 and 3 on the quotient
+    const uint32_t target = divide_exact(num, range);
+    uint32_t rem = target - below1, room = above1 - target;
+    if (GPUAR_DEC_SPEC & 4) {
+        // the four leaf nodes below (c0, c1) were requested before the quotient existed
+        const uint32_t z0 = (uint32_t)n2, z1 = (uint32_t)(n2 >> 32);
+        const uint32_t rr = rem * 0x10001u + 0x80008000u;
+        const uint32_t dlo = rr - z0, dhi = rr - z1;               // bit 31 / 15: rem >= slot (tree_level)
+        const uint32_t j0 = ~mask(dlo), j1 = ~mask(dhi << 16), j2 = ~mask(dhi);
+        const uint32_t lo3 = pick4(j0, j1, j2, (uint32_t)a3, (uint32_t)b3, (uint32_t)c3n, (uint32_t)d3n);
+        const uint32_t hi3 = pick4(j0, j1, j2, (uint32_t)(a3 >> 32), (uint32_t)(b3 >> 32), (uint32_t)(c3n >> 32),
+                                   (uint32_t)(d3n >> 32));
+        const uint32_t c2 = tree_level(n2, rem, room);
+        *p2 = n2;
+        uint64_t v = ((uint64_t)hi3 << 32) | lo3;
+        idx = idx * 4u + c2;
+        uint64_t *n = nodes + (20u + idx) * stride;
+        idx = idx * 4u + tree_level(v, rem, room);
+        *n = v;
+    } else {
+        idx = idx * 4u + tree_level(n2, rem, room);
+        *p2 = n2;
+        uint64_t *n = nodes + (20u + idx) * stride;
+        uint64_t v = *n;
+        idx = idx * 4u + tree_level(v, rem, room);
+        *n = v;
+    }
+    lo = target - rem;
+    cnt = rem + room;
+    return idx;
+}
+
 GPUAR_HD uint32_t tree_decode_early_range(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t code,
                                           uint32_t L, uint32_t range, uint32_t T, uint32_t &lo, uint32_t &cnt)
 {
+    if (GPUAR_DEC_SPEC) return tree_decode_spec_range(root, nodes, stride, code, L, range, T, lo, cnt);
     const uint32_t num = (((code - L) & 0xFFFFu) + 1u) * T - 1u;
     // "threshold * range <= num" as the sign of num - threshold * range (everything < 2^30): one
     // multiply-add and one shift per threshold, no predicates (their write-to-use latency is

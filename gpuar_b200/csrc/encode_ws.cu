@@ -20,6 +20,9 @@
 // double buffered per round of 32 positions and handed over with named barriers
 // (bar.arrive on the producer side, bar.sync on the consumer side).  The three model rings
 // share one full barrier per buffer (128 threads: three producers + CODER).
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -31,13 +34,17 @@ namespace gpuar {
 
 constexpr uint32_t kRound = 32;
 constexpr uint32_t kCoderBlock = GPUAR_WS_CODER_BLOCK;
-#ifndef GPUAR_WS_WARPS
-#define GPUAR_WS_WARPS 6            // tuning knob: warps per CTA (6 or 8; warps without a role exit at once)
-#endif
-#ifndef GPUAR_WS_ROLE_MAP
-#define GPUAR_WS_ROLE_MAP 0xFF543210u   // tuning knob: nibble w = role of warp w (0xF = none): which roles share a scheduler
-#endif
-constexpr uint32_t kWsThreads = 32u * GPUAR_WS_WARPS;
+// Role placement.  A warp's scheduler (SM sub-partition) is its index in the CTA modulo 4, so the
+// CTA is launched with six or eight warps and a role map says what each one does: nibble w of
+// the map = role of warp w, 0xF = none (the warp exits at once).  Which roles share a scheduler
+// matters: with one CTA per SM (up to 148 x 32 packets = 37 MiB) the CODER chain alone on its
+// scheduler is 7.5 % faster (128 -> 118 cycles per step); with two CTAs per SM the six-warp CTA
+// -- whose second copy the hardware places on the complementary slots -- is
+// (profiles/r1_s2_ws_rolemap.jsonl).  GPUAR_B200_WS_TUNE="warps,map_first,map_later" (hex maps)
+// overrides the choice; CTAs of the first wave (one per SM) take map_first, the others map_later.
+constexpr uint32_t kWsMaxThreads = 256;
+constexpr uint32_t kMapSix = 0xFF543210u;       // warps 0-5 = roles 0-5: A+BITS | B+CODER | D | FIELD
+constexpr uint32_t kMapCoderAlone = 0x5F43F210u; // A+FIELD | B+BITS | D | CODER
 #ifndef GPUAR_WS_SWAP_BD
 #define GPUAR_WS_SWAP_BD 0          // tuning knob: which of warps 1 / 2 takes level 2 and which the leaves
 #endif
@@ -140,14 +147,15 @@ __device__ __forceinline__ void model_warp(WsShared &sm, uint64_t *tree, const u
     }
 }
 
-__global__ void __launch_bounds__(kWsThreads)
+__global__ void __launch_bounds__(kWsMaxThreads)
 encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ slots, uint32_t slot_stride,
-                 uint32_t *__restrict__ sizes, uint32_t n_packets, uint32_t packet)
+                 uint32_t *__restrict__ sizes, uint32_t n_packets, uint32_t packet, uint32_t map_first,
+                 uint32_t map_later, uint32_t first_ctas)
 {
     extern __shared__ __align__(16) uint8_t ws_smem[];           // 72 KB: above the static limit
     WsShared &sm = *reinterpret_cast<WsShared *>(ws_smem);
     const uint32_t lane = lane_id();
-    const uint32_t role = (GPUAR_WS_ROLE_MAP >> (4u * (threadIdx.x >> 5))) & 0xFu;
+    const uint32_t role = ((blockIdx.x < first_ctas ? map_first : map_later) >> (4u * (threadIdx.x >> 5))) & 0xFu;
     const uint32_t my = blockIdx.x * 32u + lane;
     const bool mine = my < n_packets;
     const size_t off = (size_t)my * packet;
@@ -320,8 +328,23 @@ cudaError_t launch_encode_slots_ws(const uint8_t *d_in, size_t n, uint8_t *d_slo
     cudaError_t e = cudaFuncSetAttribute(encode_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(WsShared));
     if (e != cudaSuccess) return e;
-    encode_ws_kernel<<<(packets + 31u) / 32u, kWsThreads, sizeof(WsShared), st>>>(d_in, n, d_slots, slot_stride,
-                                                                                   d_sizes, packets, packet);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t ctas = (packets + 31u) / 32u;
+    struct Tune { uint32_t warps, first, later; };
+    static const Tune forced = [] {
+        Tune t{0, 0, 0};
+        if (const char *e = getenv("GPUAR_B200_WS_TUNE")) {
+            unsigned w = 0, a = 0, b = 0;
+            if (sscanf(e, "%u,%x,%x", &w, &a, &b) == 3 && (w == 6 || w == 8)) t = Tune{w, a, b};
+        }
+        return t;
+    }();
+    Tune t = ctas <= (uint32_t)sms ? Tune{8, kMapCoderAlone, kMapCoderAlone} : Tune{6, kMapSix, kMapSix};
+    if (forced.warps) t = forced;
+    encode_ws_kernel<<<ctas, 32u * t.warps, sizeof(WsShared), st>>>(d_in, n, d_slots, slot_stride, d_sizes, packets,
+                                                                     packet, t.first, t.later, (uint32_t)sms);
     count_launch();
     return cudaGetLastError();
 }
