@@ -34,14 +34,17 @@ namespace gpuar {
 
 constexpr uint32_t kRound = 32;
 constexpr uint32_t kCoderBlock = GPUAR_WS_CODER_BLOCK;
-// Role placement.  A warp's scheduler (SM sub-partition) is its index in the CTA modulo 4, so the
-// CTA is launched with six or eight warps and a role map says what each one does: nibble w of
-// the map = role of warp w, 0xF = none (the warp exits at once).  Which roles share a scheduler
-// matters: with one CTA per SM (up to 148 x 32 packets = 37 MiB) the CODER chain alone on its
-// scheduler is 7.5 % faster (128 -> 118 cycles per step); with two CTAs per SM the six-warp CTA
-// -- whose second copy the hardware places on the complementary slots -- is
-// (profiles/r1_s2_ws_rolemap.jsonl).  GPUAR_B200_WS_TUNE="warps,map_first,map_later" (hex maps)
-// overrides the choice; CTAs of the first wave (one per SM) take map_first, the others map_later.
+// Role placement.  The CTA is launched with six or eight warps and a role map says what each one
+// does: nibble w of the map = role of warp w, 0xF = none (the warp exits at once).  Which roles
+// share a scheduler (SM sub-partition; warp index modulo 4 for a CTA alone on its SM) matters:
+// with one CTA per SM (up to 148 x 32 packets = 37 MiB, and every chunk of the host-buffer
+// pipeline) eight warps with the CODER chain alone on its scheduler take 118 instead of 128
+// cycles per step; with two or three CTAs per SM every eight-warp placement measured was slower
+// than the plain six-warp CTA (0.65-0.80 against 0.624 ms at 64 MiB; how the hardware spreads a
+// second CTA's warps over the sub-partitions is not the simple rule above), so that one stays
+// (profiles/r1_s2_ws_rolemap*.jsonl).  GPUAR_B200_WS_TUNE="warps,map_first,map_later" (hex maps)
+// overrides the choice for experiments; the CTAs of the first wave (one per SM) take map_first,
+// the others map_later.
 constexpr uint32_t kWsMaxThreads = 256;
 constexpr uint32_t kMapSix = 0xFF543210u;       // warps 0-5 = roles 0-5: A+BITS | B+CODER | D | FIELD
 constexpr uint32_t kMapCoderAlone = 0x5F43F210u; // A+FIELD | B+BITS | D | CODER
