@@ -639,10 +639,15 @@ GPUAR_HD void enc_tree_init(uint64_t &root, uint64_t *nodes, uint32_t stride)
     for (uint32_t q = 0; q < 64; ++q, ++n) nodes[n * stride] = enc_leaf_init();
 }
 
+// Node increments of the encoder (a constant-memory table of the four increments instead of the
+// variable 64-bit shift was measured: the per-lane index replays the LDC, slower everywhere).
+GPUAR_HD void bump_above(uint64_t &node, uint32_t c) { node += 0x0001000100010000ull << (16u * c); }   // +1 on every slot above c
+GPUAR_HD void bump_at(uint64_t &node, uint32_t c) { node += 1ull << (16u * c); }                       // +1 on slot c
+
 GPUAR_HD uint32_t enc_upper(uint64_t &node, uint32_t c)   // slot c, then +1 above c
 {
     const uint32_t below = prmt((uint32_t)node, (uint32_t)(node >> 32), 0x0010u + 0x0022u * c);
-    node += 0x0001000100010000ull << (16u * c);
+    bump_above(node, c);
     return below;
 }
 
@@ -684,7 +689,7 @@ GPUAR_HD uint32_t tree_encode_leaf_at(uint64_t *node3, uint32_t c, uint32_t &cnt
     const uint32_t s012 = s01 + (h & 0xFFFFu);
     const uint32_t acc = prmt(x << 16, s01 | (s012 << 16), 0x0010u + 0x0022u * c);
     cnt = prmt(l, h, 0x3210u + 0x2222u * c) & 0xFFFFu;
-    n3 += 1ull << (16u * c);
+    bump_at(n3, c);
     *node3 = n3;
     return acc;
 }
@@ -735,7 +740,7 @@ GPUAR_HD uint32_t tree_encode_lower(uint64_t *nodes, uint32_t stride, uint32_t s
     const uint32_t s012 = s01 + (h & 0xFFFFu);
     acc += prmt(x << 16, s01 | (s012 << 16), 0x0010u + 0x0022u * c);
     cnt = prmt(l, h, 0x3210u + 0x2222u * c) & 0xFFFFu;
-    n3 += 1ull << (16u * c);
+    bump_at(n3, c);
     *p2 = n2;
     *p3 = n3;
     return acc;
