@@ -17,6 +17,8 @@
 // right of the path) in the same pass (coder_math.h: tree_level).  Interval arithmetic and
 // renormalisation are the single-normalisation step of coder_math.h (narrow_total: state =
 // lower bound and range); bits come from a 64-bit reservoir fed by 32-bit words.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -55,8 +57,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // kRingFeed selects how the bit window is refilled:
 //   true   cp.async ring + predicated feed: nothing in the step ever waits on a global load and
-//          there is no divergent branch -- shortest dependent chain; used when the input is at
-//          most one resident wave (each scheduler holds ~1 warp and latency is everything);
+//          there is no divergent branch -- shortest dependent chain; used while every warp has a
+//          scheduler to itself (up to 4 warps per SM = 148 MiB: latency is everything);
 //   false  one word prefetched in a register, fed under a (divergent) branch -- fewer
 //          instructions per step; used when many warps per scheduler hide the latency.
 template <bool kRingFeed>
@@ -202,7 +204,14 @@ cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint6
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t grid = (packets + 31u) / 32u;
-    if (grid <= (uint32_t)sms * 10u)             // at most one resident wave: latency-optimised feed
+    // tuning aid: GPUAR_B200_DEC_RING_MAX=<CTAs> moves the switch between the two variants
+    static const long forced = [] { const char *e = getenv("GPUAR_B200_DEC_RING_MAX"); return e ? atol(e) : -1L; }();
+    // The latency-optimised variant pays for its short chain with 246 instructions per step (the
+    // other one: 177).  It wins while every warp has a scheduler to itself (4 per SM: 1.67 against
+    // 2.55 ms at 128 MiB) and loses as soon as two warps share one (2.95 against 2.72 ms at 192 MiB,
+    // 4.41 against 3.30 ms at 368 MiB; profiles/r1_s2_dec_switch.txt).
+    const uint32_t ring_max = forced >= 0 ? (uint32_t)forced : (uint32_t)sms * 4u;
+    if (grid <= ring_max)
         decode_kernel<true><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet);
     else
         decode_kernel<false><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet);
