@@ -205,7 +205,7 @@ cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint6
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t grid = (packets + 31u) / 32u;
     // tuning aid: GPUAR_B200_DEC_RING_MAX=<CTAs> moves the switch between the two variants
-    static const long forced = [] { const char *e = getenv("GPUAR_B200_DEC_RING_MAX"); return e ? atol(e) : -1L; }();
+    static const long forced = [] { const char *e = getenv("GPUAR_B200_DEC_RING_MAX"); return e && *e ? atol(e) : -1L; }();
     // The latency-optimised variant pays for its short chain with 246 instructions per step (the
     // other one: 177).  It wins while every warp has a scheduler to itself (4 per SM: 1.67 against
     // 2.55 ms at 128 MiB) and loses as soon as two warps share one (2.95 against 2.72 ms at 192 MiB,
