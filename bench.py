@@ -41,6 +41,7 @@ WORKLOADS = {
     "s1g": ("and3", 2, 1 << 30, "and3(2, 1 GiB) low-entropy (BASELINE config 3)"),
     "m2g": ("mixed", 3, 2 << 30, "mixed(3, 2 GiB per rank) (BASELINE config 4 shard)"),
     "m4g": ("mixed", 7, 4 << 30, "mixed(7, 4 GiB) (BASELINE config 5)"),
+    "m16g": ("mixed", 3, 16 << 30, "mixed(3, 16 GiB) (BASELINE config 4, whole job on one rank)"),
     # tuning only (where the warp-specialised encoder hands over to the lane=packet one)
     "u128m": ("uniform", 0x65, 128 << 20, "uniform(0x65, 128 MiB) (tuning)"),
     "u192m": ("uniform", 0x66, 192 << 20, "uniform(0x66, 192 MiB) (tuning)"),
@@ -285,12 +286,11 @@ def run_ours(args):
     gen, seed, nbytes, desc = WORKLOADS[args.workload]
     # weak scaling: the job is `world` times the per-rank workload; rank r owns packets [r*P, (r+1)*P)
     start = rank * nbytes
-    if gen == "uniform":
-        x = D.uniform_device(seed, nbytes, start)
-    elif gen == "and3":
-        x = D.and3_device(seed, nbytes, start)
-    else:
-        x = D.mixed_device(seed, nbytes, start)
+    x = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    gen_dev = {"uniform": D.uniform_device, "and3": D.and3_device, "mixed": D.mixed_device}[gen]
+    for a in range(0, nbytes, 1 << 29):                            # 512 MiB at a time: bounded temporaries
+        b = min(nbytes, a + (1 << 29))
+        x[a:b] = gen_dev(seed, b - a, start + a)
     packet = args.packet
     packets = (nbytes + packet - 1) // packet
     cap = codec.payload_bound(nbytes, packet)

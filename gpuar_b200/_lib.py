@@ -52,6 +52,7 @@ SIGNATURES = {
     "gpuar_b200_compress_host": (C.c_int, [_vp, _sz, _vp, _sz, C.POINTER(_sz)]),
     "gpuar_b200_decompress_host": (C.c_int, [_vp, _sz, _vp, _sz, C.POINTER(_sz)]),
     "gpuar_b200_gip_raw_size": (C.c_int, [_vp, _sz, C.POINTER(C.c_uint64)]),
+    "gpuar_b200_gip_walk": (C.c_int, [_vp, _sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gpuar_b200_write_header": (None, [_vp, C.c_uint64, C.c_uint64]),
     "gpuar_b200_check_header": (C.c_int, [_vp]),
     "gpuar_b200_peer_concat": (C.c_int, [_vp, C.c_int, _sz, _vp, C.c_int, _sz, _vp]),

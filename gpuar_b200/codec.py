@@ -180,14 +180,26 @@ def raw_size(gip) -> int:
     return int(raw.value)
 
 
+def walk(gip) -> tuple[int, int]:
+    """(packets, raw bytes) of a .gip image by hopping over its packet headers on the host."""
+    g = _as_u8(gip)
+    packets, raw = C.c_uint64(0), C.c_uint64(0)
+    check(lib().gpuar_b200_gip_walk(g.ctypes.data, g.size, C.byref(packets), C.byref(raw)), "gpuar_b200_gip_walk")
+    return int(packets.value), int(raw.value)
+
+
 def decompress(gip, out: np.ndarray | None = None, out_cap: int | None = None) -> np.ndarray:
     """Inverse of :func:`compress`, via gpuar_b200_decompress_host."""
     init()
     g = _as_u8(gip)
     if out is None:
         if out_cap is None:
-            # the header field is 32 bit in reference-written files: size by the payload instead
-            out_cap = max(raw_size(g), 0) if g.size < (1 << 32) else (g.size // 5 + 1) * PACKET
+            # The header field is 32 bit in reference-written files.  Images written by this library
+            # carry (and mark) the high half; for an unmarked image that could hold 4 GiB or more the
+            # size comes from a hop over its packet headers (one read per packet).
+            out_cap = raw_size(g)
+            if g.size >= (1 << 32) - (1 << 28) and (g[3] != 0xB2 or out_cap < (1 << 32)):
+                out_cap = walk(g)[1]
         out = np.empty(out_cap + PACKET, dtype=np.uint8)
     n_out = C.c_size_t(0)
     check(lib().gpuar_b200_decompress_host(g.ctypes.data, g.size, out.ctypes.data, out.size, C.byref(n_out)),

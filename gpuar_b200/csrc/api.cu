@@ -212,6 +212,7 @@ int gpuar_b200_encode_ex(const uint8_t *d_in, size_t n, size_t packet_bytes, uin
     if (payload_cap < gpuar_b200_payload_bound_ex(n, packet_bytes) || scratch_bytes < p.total) return GPUAR_E_ARG;
     if (p.packets > 0xFFFFFFF0ull) return GPUAR_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return ck(cudaMemsetAsync(d_payload_bytes, 0, sizeof(uint64_t), st));   // no packets: scratch may be NULL
     uint8_t *s = static_cast<uint8_t *>(d_scratch);
     uint32_t *sizes = d_packet_sizes ? d_packet_sizes : reinterpret_cast<uint32_t *>(s + p.off_sizes);
     cudaError_t e;
@@ -368,6 +369,7 @@ void gpuar_b200_write_header(uint8_t hdr[20], uint64_t raw_bytes, uint64_t gip_b
 {
     memset(hdr, 0, GPUAR_FILE_HEADER);
     hdr[0] = 0; hdr[1] = 1; hdr[2] = 0;                 /* file_header.hpp:25-27,33-35 */
+    hdr[3] = GPUAR_HEADER_WIDE_MARK;                    /* never written by the reference: marks 64-bit size fields */
     for (int k = 0; k < 8; ++k) {
         hdr[4 + k] = (uint8_t)(raw_bytes >> (8 * k));   /* :61-66 defines the low 4 bytes */
         hdr[12 + k] = (uint8_t)(gip_bytes >> (8 * k));  /* :67-72 */
@@ -388,12 +390,36 @@ int gpuar_b200_gip_raw_size(const uint8_t *gip, size_t gip_bytes, uint64_t *raw_
         lo |= (uint64_t)gip[4 + k] << (8 * k);
         hi |= (uint64_t)gip[8 + k] << (8 * k);
     }
-    /* bytes 8-11 are uninitialised in reference-written files: trust them only if the
-     * resulting size is plausible for this payload (each packet holds <= 8192 raw bytes
-     * and occupies >= 5 bytes) */
+    /* bytes 3 and 8-11 are uninitialised in reference-written files: the high half is trusted only
+     * under this library's mark in byte 3 AND if the resulting size is plausible for this payload:
+     * a stream of P full packets holds more than (P-1)*8192 raw bytes, P <= payload/210 + 1 (8192
+     * equal bytes code into 210), and arithmetic coding with this model expands by < 7 % */
     const uint64_t payload = gip_bytes - GPUAR_FILE_HEADER;
     const uint64_t wide = lo | (hi << 32);
-    *raw_bytes = (hi && wide <= (payload / 5 + 1) * (uint64_t)kPacket) ? wide : lo;
+    const bool marked = gip[3] == GPUAR_HEADER_WIDE_MARK;
+    const bool plausible = wide <= (payload / 210 + 1) * (uint64_t)kPacket && wide + wide / 14 + kSlot >= payload;
+    *raw_bytes = (hi && marked && plausible) ? wide : lo;
+    return 0;
+}
+
+int gpuar_b200_gip_walk(const uint8_t *gip, size_t gip_bytes, uint64_t *packets, uint64_t *raw_bytes)
+{
+    if (!gip || gip_bytes < GPUAR_FILE_HEADER || gpuar_b200_check_header(gip)) return GPUAR_E_FORMAT;
+    const uint8_t *pay = gip + GPUAR_FILE_HEADER;
+    const size_t c = gip_bytes - GPUAR_FILE_HEADER;
+    uint64_t n = 0, raw = 0;
+    for (size_t pos = 0; pos < c;) {                     /* cpu_compressor.cpp:47-78: the chain is the only index */
+        if (c - pos < kHdr) return GPUAR_E_FORMAT;
+        const size_t len = (size_t)pay[pos] | ((size_t)pay[pos + 1] << 8);
+        const size_t r = (size_t)pay[pos + 2] | ((size_t)pay[pos + 3] << 8);
+        if (len <= kHdr || len > c - pos) return GPUAR_E_FORMAT;
+        if (r == 0 || r > kPacket) return GPUAR_E_UNSUPPORTED;
+        ++n;
+        raw += r;
+        pos += len;
+    }
+    if (packets) *packets = n;
+    if (raw_bytes) *raw_bytes = raw;
     return 0;
 }
 
@@ -525,14 +551,16 @@ int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *ou
         return h->offsets.need(want * sizeof(uint64_t));
     };
     if ((e = reserve_offsets(max_packets, 0)) != cudaSuccess) return ck(e);
-    // device mirror of the output: chunk k lands at its raw offset rounded up to 16 bytes
-    const size_t chunks_bound = c / chunk_bytes + 2;
-    if ((e = h->big_out.need(out_cap + 16 * chunks_bound + kPacket + 64)) != cudaSuccess) return ck(e);
-    if ((e = cudaMemsetAsync(d_pay + c, 0, GPUAR_PAD_BYTES, h->stream[0])) != cudaSuccess) return ck(e);
-    if ((e = cudaEventRecord(h->ready, h->stream[0])) != cudaSuccess) return ck(e);
     // a chunk of full packets holds at most chunk_bytes / 210 of them (8192 equal bytes code into
     // 210); the bound only cuts chunks of short packets, whose scratch is sized by the packet count
     const size_t chunk_packets = chunk_bytes / 128 + 1024;
+    // device mirror of the output: chunk k lands at its raw offset rounded up to 16 bytes.  Chunks end
+    // after chunk_bytes of payload or chunk_packets packets (a packet is at least 5 bytes), so there
+    // are at most this many of them; every launch is checked against the capacity again below.
+    const size_t chunks_bound = c / chunk_bytes + (c / 5) / chunk_packets + 3;
+    if ((e = h->big_out.need(out_cap + 16 * chunks_bound + kPacket + 64)) != cudaSuccess) return ck(e);
+    if ((e = cudaMemsetAsync(d_pay + c, 0, GPUAR_PAD_BYTES, h->stream[0])) != cudaSuccess) return ck(e);
+    if ((e = cudaEventRecord(h->ready, h->stream[0])) != cudaSuccess) return ck(e);
 
     // errors in mid-stream: nothing may still be reading the caller's buffers (or ours) on return
     auto fail = [&](int code) { drain_all(); return code; };
@@ -584,6 +612,8 @@ int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *ou
         if (e != cudaSuccess) return fail(ck(e));
         uint8_t *d_out = (uint8_t *)h->big_out.p + dev0;
         dev_pos = align_up(dev0 + (total - raw0), 16);
+        // the strided decode writes whole 8192-byte rows for every packet but the chunk's last
+        if (dev0 + (ragged ? total - raw0 : (m - 1) * (size_t)kPacket + last_raw) > h->big_out.cap) return fail(GPUAR_E_ARG);
         if (!ragged) {
             rc = gpuar_b200_decode(d_pay, c, d_off, m, d_out, m * (size_t)kPacket, st);
         } else {

@@ -42,6 +42,12 @@ class File {                                   // RAII FILE*
     File(const File &) = delete;
     File &operator=(const File &) = delete;
     std::FILE *get() const { return f_; }
+    void close(const char *what)                   // flush + close with the error reported (ENOSPC shows up here)
+    {
+        std::FILE *f = f_;
+        f_ = nullptr;
+        if (f && (std::fflush(f) != 0 || std::fclose(f) != 0)) throw std::runtime_error(what);
+    }
     std::uint64_t size()
     {
         const long at = std::ftell(f_);

@@ -11,6 +11,7 @@ static void putHeader(std::uint8_t h[kFileHeader], std::uint64_t raw, std::uint6
 {
     std::memset(h, 0, kFileHeader);
     h[1] = 1;                                              // version 0.1.0, file_header.hpp:25-27
+    h[3] = 0xB2;                                           // GPUAR_HEADER_WIDE_MARK: bytes 8-11 / 16-19 hold the high halves
     for (int k = 0; k < 8; ++k) {
         h[4 + k] = (std::uint8_t)(raw >> (8 * k));
         h[12 + k] = (std::uint8_t)(total >> (8 * k));
@@ -47,6 +48,7 @@ CompressionInfo CpuCompressor::compress(ProgressMonitor *monitor)
     putHeader(header, info.uncompressedFileSize, info.compressedFileSize);
     if (std::fseek(out.get(), 0, SEEK_SET) != 0 || std::fwrite(header, kFileHeader, 1, out.get()) != 1)
         throw std::runtime_error("Write data to file failed");
+    out.close("Write data to file failed");
     info.processTime = proc.ms();
     info.ioTime = io.ms();
     return info;
@@ -84,6 +86,7 @@ CompressionInfo CpuCompressor::decompress(ProgressMonitor *monitor)
         info.processedUncompressedSize += n;
         monitor->updateProgress(&info);
     }
+    out.close("Write raw data to file failed");
     info.uncompressedFileSize = info.processedUncompressedSize;
     info.processTime = proc.ms();
     info.ioTime = io.ms();

@@ -53,7 +53,7 @@ void GpuCompressor::chooseDevice(int id)
     device_ = id;
 }
 
-void GpuCompressor::reserve(std::size_t inBytes, std::size_t outBytes)
+void GpuCompressor::reserve(std::size_t inBytes, std::size_t outBytes, bool secondInput)
 {
     // Page-locking is the expensive part of start-up (the kernel faults in and pins every page,
     // ~0.7 s per GiB on the B200 hosts), and the four buffers pin independently: one helper
@@ -61,7 +61,8 @@ void GpuCompressor::reserve(std::size_t inBytes, std::size_t outBytes)
     // device 0.
     const auto t0 = std::chrono::steady_clock::now();
     std::uint8_t **slot[4] = {&in_[0], &in_[1], &out_[0], &out_[1]};
-    const std::size_t want[4] = {inBytes > inCap_ ? inBytes : 0, inBytes > inCap_ ? inBytes : 0,
+    // the decode path reads into in_[0] only (one sliding window): in_[1] is not pinned for it
+    const std::size_t want[4] = {inBytes > inCap_ ? inBytes : 0, secondInput && inBytes > inCap1_ ? inBytes : 0,
                                  outBytes > outCap_ ? outBytes : 0, outBytes > outCap_ ? outBytes : 0};
     std::future<int> pinned[4];
     const int device = device_;
@@ -86,6 +87,7 @@ void GpuCompressor::reserve(std::size_t inBytes, std::size_t outBytes)
             if (r && !rc) rc = r;
         }
     if (want[0]) inCap_ = rc ? 0 : inBytes;
+    if (want[1]) inCap1_ = rc ? 0 : inBytes;
     if (want[2]) outCap_ = rc ? 0 : outBytes;
     check(rc, "gpuar_b200_host_alloc");
     trace("page-locked staging", t0);
@@ -106,7 +108,7 @@ CompressionInfo GpuCompressor::compress(ProgressMonitor *monitor)
     info.compressedFileSize = kFileHeader;
 
     const std::size_t seg = std::min<std::size_t>(segmentBytes_, std::max<std::size_t>(info.uncompressedFileSize, 1));
-    reserve(seg + 16, kFileHeader + gpuar_b200_payload_bound(seg));
+    reserve(seg + 16, kFileHeader + gpuar_b200_payload_bound(seg), true);
     // three-stage pipeline over segments: read(i+1) | device(i) | write(i-1)
     auto readSegment = [&](int b) { return std::fread(in_[b], 1, seg, in.get()); };
     auto writeSegment = [&](int b, std::size_t payload) {
@@ -146,6 +148,7 @@ CompressionInfo GpuCompressor::compress(ProgressMonitor *monitor)
     gpuar_b200_write_header(header, info.uncompressedFileSize, info.compressedFileSize);
     if (std::fseek(out.get(), 0, SEEK_SET) != 0 || std::fwrite(header, kFileHeader, 1, out.get()) != 1)
         throw std::runtime_error("Write data to file failed");
+    out.close("Write data to file failed");                      // a full disk shows up here at the latest
     io.stop();
     info.processTime = proc.ms();
     info.ioTime = io.ms();
@@ -184,7 +187,7 @@ CompressionInfo GpuCompressor::decompress(ProgressMonitor *monitor)
     const std::size_t segRaw = (std::size_t)std::min<std::uint64_t>(
         segmentBytes_, (hint + kPacketBytes - 1) / kPacketBytes * kPacketBytes);
     const std::size_t segPayload = (std::size_t)std::min<std::uint64_t>(segRaw + segRaw / 16, payloadBytes + kSlotBytes);
-    reserve(kFileHeader + segPayload + kSlotBytes + 64, segRaw + 4 * kPacketBytes);
+    reserve(kFileHeader + segPayload + kSlotBytes + 64, segRaw + 4 * kPacketBytes, false);
     // window [begin, end) of the staging buffer holds payload bytes not yet decoded
     std::size_t begin = 0, end = 0;
     std::uint64_t remaining = fileBytes - kFileHeader;
@@ -240,6 +243,7 @@ CompressionInfo GpuCompressor::decompress(ProgressMonitor *monitor)
     }
     io.start();
     if (writing.valid() && !writing.get()) throw std::runtime_error("Write uncompressed data to output file failed");
+    out.close("Write uncompressed data to output file failed");
     io.stop();
     info.uncompressedFileSize = produced;
     info.processTime = proc.ms();

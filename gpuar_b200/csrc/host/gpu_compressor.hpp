@@ -10,11 +10,11 @@ class GpuCompressor : public Compressor {
     // read from the input file and segment i-1 is written to the output file by helper threads
     std::uint8_t *in_[2] = {nullptr, nullptr};
     std::uint8_t *out_[2] = {nullptr, nullptr};
-    std::size_t inCap_ = 0, outCap_ = 0;
+    std::size_t inCap_ = 0, inCap1_ = 0, outCap_ = 0;
     std::size_t segmentBytes_;         // raw bytes handled per library call (multiple of 8192)
     int device_ = -1;                  // chooseDevice() argument; -1 = the process default (device 0)
 
-    void reserve(std::size_t inBytes, std::size_t outBytes);
+    void reserve(std::size_t inBytes, std::size_t outBytes, bool secondInput);
 
   public:
     explicit GpuCompressor(std::size_t segmentBytes = (std::size_t)128 << 20);

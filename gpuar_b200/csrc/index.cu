@@ -366,6 +366,7 @@ cudaError_t launch_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets
     if (c) {
         // at most one packet per 5 payload bytes; well-formed streams have far fewer
         const size_t upper = max_packets < c / 5 + 1 ? max_packets : c / 5 + 1;
+        if (upper == 0) return cudaGetLastError();                 // no room for offsets: result[2] already says E_ARG
         index_rank_kernel<<<(unsigned)((upper + 255) / 256), 256, 0, st>>>(cand, p.cap, ctl, jump, p.levels,
                                                                            d_offsets, max_packets, d_result);
         count_launch();

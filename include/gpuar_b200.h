@@ -40,6 +40,9 @@ extern "C" {
 #define GPUAR_PACKET_HEADER 4u    /* PACKET_HEADER_LENGTH     */
 #define GPUAR_FILE_HEADER 20u     /* FileHeader::HEADER_LENGTH */
 #define GPUAR_PAD_BYTES 64u       /* readable slack required past a payload (decoder over-read) */
+#define GPUAR_HEADER_WIDE_MARK 0xB2u /* header byte 3 (never written by the reference, file_header.hpp:28-36):
+                                        set by this library when bytes 8-11 / 16-19 carry the high halves of
+                                        64-bit sizes */
 
 #define GPUAR_E_ARG (-1)          /* bad argument / buffer too small            */
 #define GPUAR_E_FORMAT (-2)       /* malformed .gip header or packet chain      */
@@ -63,7 +66,10 @@ size_t gpuar_b200_index_scratch_bytes(size_t c);  /* device scratch for gpuar_b2
  * d_in[n] -> d_payload (packets compacted on the device, no 20-byte header).
  * Replaces garCompressExecutor (gpuar.h:77) + the per-packet D2H/fwrite loop
  * (gpu_compressor.cpp:136-169).
- *   d_in            16-byte aligned.
+ *   d_in            16-byte aligned and READABLE up to n rounded up to 16: the kernels fetch the
+ *                   input as 16-byte words, so the last fetch may read up to 15 bytes past n (their
+ *                   values are ignored).  The same holds for garCompressExecutor below, as it does
+ *                   for the reference's own kernel (gpuar_kernel.cu:496-517 reads ulonglong2 words).
  *   d_payload       16-byte aligned, capacity >= gpuar_b200_payload_bound(n).
  *   d_payload_bytes device u64: total payload length C.
  *   d_packet_sizes  optional device u32[packets]: compLen of each packet (may be NULL).
@@ -141,9 +147,16 @@ int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *ou
  * reference's layout, 64-bit when written by this library -- see DESIGN.md). */
 int gpuar_b200_gip_raw_size(const uint8_t *gip, size_t gip_bytes, uint64_t *raw_bytes);
 
+/* The same by hopping over the compLen / rawLen fields of the whole image in host memory, as the
+ * reference's CPU decoder finds its packets (cpu_compressor.cpp:47-78): exact for any stream,
+ * including reference-written images of 4 GiB and more whose 32-bit header field has wrapped.
+ * One u32 read per packet; validates the chain (GPUAR_E_FORMAT / GPUAR_E_UNSUPPORTED). */
+int gpuar_b200_gip_walk(const uint8_t *gip, size_t gip_bytes, uint64_t *packets, uint64_t *raw_bytes);
+
 /* 20-byte header, byte-compatible with file_header.hpp:28-36,61-72 in every byte the
  * reference defines; the bytes it leaves uninitialised carry the high halves of the
- * 64-bit sizes (zero below 4 GiB). */
+ * 64-bit sizes (zero below 4 GiB) and, in byte 3, GPUAR_HEADER_WIDE_MARK, without which a
+ * reader must not trust them. */
 void gpuar_b200_write_header(uint8_t hdr[20], uint64_t raw_bytes, uint64_t gip_bytes);
 int gpuar_b200_check_header(const uint8_t hdr[20]);
 

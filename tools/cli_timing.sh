@@ -17,6 +17,7 @@ PY
 out=gpurun_out/${tag}_cli_timing.txt
 echo "GPUs visible: $(nvidia-smi -L | wc -l); host threads: $(nproc)" > $out
 export GPUAR_B200_TRACE=1       # start-up costs (context, page-locking) on stderr
+export GPUAR_B200_FAST_EXIT=1   # end the process without the CUDA teardown (opt-in; the default is orderly)
 run() {
   echo "\$ gpuar $*" >> $out
   local t0=$(date +%s%N)
