@@ -1,22 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- encode/decode throughput of the GPUAR hot path on B200 (contract in the task brief).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--sub A,B]
 
 A step is one pass of the hot path over one batch of synthetic input.  K encode steps
 (model+coder kernel, size scan + compaction) and K decode steps (device packet-chain discovery +
 decode kernel) are timed separately with CUDA events on the launching stream, inputs resident in
 HBM; L2 is flushed between timed iterations.  `value` is encode GB/s (uncompressed bytes / time,
 GB = 1e9 B, whole job over all ranks); decode GB/s is reported beside it under "decode".
-`e2e` is the same encode metric through gpuar_b200_compress_host from pinned HOST buffers
+`e2e` is the same encode metric from pinned HOST buffers through the library's host entry points
 (H2D + kernels + D2H inside the timed region); "e2e_decode" likewise.
 
-Workloads: u64m = uniform(0x64, 64 MiB) (BASELINE config 2, the default),
-s1g = and3(2, 1 GiB) (config 3), m2g = mixed(3, 2 GiB per rank) (config 4's per-GPU shard at 8 GPUs).
-With N > 1 (torchrun) every rank encodes its own packet range of the N-times-larger input
-(weak scaling), the ranks' payload totals are exclusive-scanned, and the streams are concatenated
-with peer stores over NVLink into W equal segments (segment g on GPU g); the gather of the whole
-stream onto one GPU and the no-exchange case are timed beside it.
+Workloads.  The headline (default) is BASELINE config 4, m16g = mixed(3, 16 GiB): ONE
+16 GiB input at every N, sharded by packet range over the N GPUs (strong scaling; it fits one B200).
+The other configurations ride in the same JSON line under "sub": u64m = uniform(0x64, 64 MiB)
+(config 2) and s1g = and3(2, 1 GiB) (config 3), each per rank (weak scaling at N > 1).
+With N > 1 (torchrun) every rank encodes its packet range with gpuar_b200_encode_sharded: the ranks'
+totals travel through peer-mapped mailboxes and the compaction kernel writes every packet straight to
+its place in the concatenated stream, laid out in N equal segments, segment g on GPU g (peer stores
+over NVLink; no NCCL call and no host round trip inside the timed region).  Decode at N > 1 is
+gpuar_b200_decode_sharded: every rank discovers the packet chain of its own segment and decodes the
+packets that start there.  The gather of the whole stream onto one GPU and the no-exchange case are
+timed beside it.
+
+Nothing is printed unless parity holds ("parity" in the line): every rank's decoded slice equals the
+regenerated input, the head of the concatenated stream has the md5 of the reference's own output for
+it (tests/golden), and at N > 1 rank 0 decodes the whole gathered stream with the single-GPU path.
 
 --impl reference times the reference's own CPU codec (oracle/_ref, compiled from the reference
 sources; falls back to the oracle port) on the host cores.
@@ -36,12 +45,12 @@ sys.path.insert(0, ROOT)
 
 GB = 1e9
 WORKLOADS = {
-    # name: (generator, seed, bytes per rank, description)
+    # name: (generator, seed, bytes, description); bytes = the whole job for STRONG workloads, per rank otherwise
+    "m16g": ("mixed", 3, 16 << 30, "mixed(3, 16 GiB), one input sharded by packet range over the GPUs (BASELINE config 4)"),
     "u64m": ("uniform", 0x64, 64 << 20, "uniform(0x64, 64 MiB) = data/random_64m.dat stand-in (BASELINE config 2)"),
     "s1g": ("and3", 2, 1 << 30, "and3(2, 1 GiB) low-entropy (BASELINE config 3)"),
-    "m2g": ("mixed", 3, 2 << 30, "mixed(3, 2 GiB per rank) (BASELINE config 4 shard)"),
+    "m2g": ("mixed", 3, 2 << 30, "mixed(3, 2 GiB per rank) (BASELINE config 4 shard, weak)"),
     "m4g": ("mixed", 7, 4 << 30, "mixed(7, 4 GiB) (BASELINE config 5)"),
-    "m16g": ("mixed", 3, 16 << 30, "mixed(3, 16 GiB) (BASELINE config 4, whole job on one rank)"),
     # tuning only (where the warp-specialised encoder hands over to the lane=packet one)
     "u128m": ("uniform", 0x65, 128 << 20, "uniform(0x65, 128 MiB) (tuning)"),
     "u192m": ("uniform", 0x66, 192 << 20, "uniform(0x66, 192 MiB) (tuning)"),
@@ -60,13 +69,33 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+STRONG = {"m16g"}             # one fixed job split over the ranks; everything else is per rank
+# md5 of the head of the reference's payload for each generator/seed (tests/golden/vectors.json: m1m, s1m, u64m)
+PREFIX_GOLDEN = {("mixed", 3): "m1m", ("and3", 2): "s1m", ("uniform", 0x64): "u64m"}
+
+
+def kernel_source_hash():
+    """sha256 over the kernel sources: ties profiles/traffic.json (ncu DRAM bytes) to the code it was captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "gpuar_b200", "csrc")
+    for name in ("coder_math.h", "common.cuh", "lookback.cuh", "shard.cuh", "encode.cu", "encode_ws.cu", "decode.cu"):
+        h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def measured_traffic(workload, kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of
-    this workload (profiles/traffic.json), or None if that workload has not been captured."""
+    """(dram__bytes_read.sum + dram__bytes_write.sum per launch, note) from the committed ncu --set full capture of
+    this workload (profiles/traffic.json).  The capture records the hash of the kernel sources it was taken from;
+    a number from other sources is not reported."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload][kernel]
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        entry = t[workload]
     except Exception:
-        return None
+        return None, "no ncu --set full capture of this workload under profiles/"
+    if entry.get("kernel_sources_sha") != kernel_source_hash():
+        return None, "profiles/traffic.json was captured from other kernel sources (stale): not reported"
+    return entry.get(kernel), f"ncu --set full capture {entry.get('capture', '?')} of these kernel sources"
 
 
 class ClockSampler:
@@ -132,6 +161,19 @@ class ClockSampler:
                 "samples": len(sm), "samples_timed": inside}
 
 
+
+def job_config(args, world):
+    """The `config` object of the JSON line: the same for both arms (the reference arm times the reference's CPU
+    codec on a bounded sample of the same workload)."""
+    gen, seed, nbytes, desc = WORKLOADS[args.workload]
+    strong = args.workload in STRONG
+    return {"workload": args.workload, "desc": desc, "job_bytes": nbytes if strong else nbytes * world,
+            "packet_bytes": args.packet, "l2": "flushed between timed iterations (256 MiB write)",
+            "parallelism": f"packet-range shards x{world}" if world > 1 else "single GPU",
+            "encode_path": args.encode_path, "work_unit_packets": args.work_unit or "auto",
+            "sub_workloads": [w for w in args.sub.split(",") if w]}
+
+
 # =============================================================== reference arm
 def run_reference(args):
     """The reference's own CPU codec on the host cores (rank 0 only)."""
@@ -173,10 +215,10 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "encode_GBps", "value": v, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_enc * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": desc, "packet_bytes": 8192},
+        "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None, "dtype": "u16",
+        "data": "synthetic", "config": job_config(args, args.gpus),
         "decode": {"value": sample / t_dec / GB, "unit": "GB/s", "ms_per_step": t_dec * 1e3},
-        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": cores, "kind": kind,
+        "cpu_baseline": {"value": v, "value_per_core": v / cores, "unit": "GB/s", "cores": cores, "kind": kind,
                          "sample": f"first {sample >> 20} MiB of the workload per step, packets partitioned over "
                                    f"{cores} host threads (the reference itself is single-threaded)"},
         "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -187,7 +229,8 @@ def run_reference(args):
 
 # ==================================================================== our arm
 def cpu_baseline(workload):
-    """Reference CPU codec on this box's host cores, bounded sample (rank 0, N=1 only)."""
+    """Reference CPU codec on this box's host cores, bounded sample (rank 0, N=1 only).  Returns the JSON object,
+    the sample and the reference's payload for it (the parity check compares our stream's head with it)."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle as O
@@ -207,13 +250,13 @@ def cpu_baseline(workload):
         t0 = time.perf_counter(); pay = O.encode(data); t_enc = time.perf_counter() - t0
         t0 = time.perf_counter(); back = O.decode(pay); t_dec = time.perf_counter() - t0
     assert np.array_equal(back, data)
-    out = {"value": sample / t_enc / GB, "unit": "GB/s", "cores": cores, "kind": kind,
-           "decode_value": sample / t_dec / GB,
+    out = {"value": sample / t_enc / GB, "value_per_core": sample / t_enc / GB / cores, "unit": "GB/s", "cores": cores,
+           "kind": kind, "decode_value": sample / t_dec / GB, "decode_value_per_core": sample / t_dec / GB / cores,
            "sample": f"first {sample >> 20} MiB of the workload, one pass, packets partitioned over {cores} host "
                      f"threads ({(t_enc + t_dec) * cores:.1f} core-seconds)"}
     if kind == "reference":
         out["reference_gpu_kernel"] = reference_gpu_kernel(data, pay)
-    return out, pay
+    return out, data, pay
 
 
 def reference_gpu_kernel(data, pay):
@@ -251,80 +294,85 @@ def reference_gpu_kernel(data, pay):
         return {"error": repr(e)}
 
 
-def run_ours(args):
-    import numpy as np
+def gen_device(gen, seed, start, n):
+    """Bytes [start, start+n) of the synthetic stream on the current device (start a multiple of 8192)."""
     import torch
-    import torch.distributed as dist
-    from gpuar_b200 import _lib, codec, datagen as D
-    from gpuar_b200.shard import ShardedCodec
+    from gpuar_b200 import datagen as D
+    fn = {"uniform": D.uniform_device, "and3": D.and3_device, "mixed": D.mixed_device}[gen]
+    out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    pos, end = start, start + n
+    while pos < end:                                               # 512 MiB at a time: bounded temporaries
+        a0 = pos // 65536 * 65536
+        b = min(end, a0 + (1 << 29))
+        b1 = (b + 65535) // 65536 * 65536
+        piece = fn(seed, b1 - a0, a0)
+        out[pos - start: b - start] = piece[pos - a0: b - a0]
+        del piece
+        pos = b
+    return out
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
-    torch.cuda.set_device(local)
-    if world > 1:
-        # NCCL announces its version on stdout at communicator creation: keep stdout for the JSON line
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
+
+def equals_stream(gen, seed, start, got):
+    """got == bytes [start, start + len(got)) of the synthetic stream, compared 512 MiB at a time."""
+    import torch
+    n = got.numel()
+    for a in range(0, n, 1 << 29):
+        b = min(n, a + (1 << 29))
+        if not torch.equal(got[a:b], gen_device(gen, seed, start + a, b - a)):
+            return False
+    return True
+
+
+class Rig:
+    """What every measurement shares: the rank, its codec, the two sharded layouts, the L2 flush buffer."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from gpuar_b200 import _lib, codec
+        from gpuar_b200.shard import ShardedCodec
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        assert self.world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={self.world}: launch with torch.distributed.run"
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            # NCCL announces its version on stdout at communicator creation: keep stdout for the JSON line.
+            # NCCL is plumbing here (setup, barriers, the max over ranks): no call inside a timed region.
             sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
-    dev = codec.DeviceCodec(local)
-    _lib.set_option(_lib.OPT_ENCODE_PATH, {"auto": 0, "fused": 1, "ws": 2}[args.encode_path])
-    if args.work_unit:
-        _lib.set_option(_lib.OPT_COMPACT_TILE, args.work_unit)
-    sharded = ShardedCodec(dev, rank, world, "segments")
-    gathered = ShardedCodec(dev, rank, world, "gather") if world > 1 else None
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
+        self.dev = codec.DeviceCodec(self.local)
+        _lib.set_option(_lib.OPT_ENCODE_PATH, {"auto": 0, "fused": 1, "ws": 2}[args.encode_path])
+        if args.work_unit:
+            _lib.set_option(_lib.OPT_COMPACT_TILE, args.work_unit)
+        self.sharded = ShardedCodec(self.dev, self.rank, self.world, "segments")
+        self.gathered = ShardedCodec(self.dev, self.rank, self.world, "gather") if self.world > 1 else None
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
 
-    gen, seed, nbytes, desc = WORKLOADS[args.workload]
-    # weak scaling: the job is `world` times the per-rank workload; rank r owns packets [r*P, (r+1)*P)
-    start = rank * nbytes
-    x = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-    gen_dev = {"uniform": D.uniform_device, "and3": D.and3_device, "mixed": D.mixed_device}[gen]
-    for a in range(0, nbytes, 1 << 29):                            # 512 MiB at a time: bounded temporaries
-        b = min(nbytes, a + (1 << 29))
-        x[a:b] = gen_dev(seed, b - a, start + a)
-    packet = args.packet
-    packets = (nbytes + packet - 1) // packet
-    cap = codec.payload_bound(nbytes, packet)
-    payload = torch.empty(cap + 16, dtype=torch.uint8, device="cuda")
-    total = torch.zeros(1, dtype=torch.int64, device="cuda")
-    offsets = torch.empty(packets + 1, dtype=torch.int64, device="cuda")
-    result = torch.zeros(4, dtype=torch.int64, device="cuda")
-    out = torch.empty(packets * packet, dtype=torch.uint8, device="cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
-    sharded.reserve(cap)
-    if gathered:
-        gathered.reserve(cap)
-
-    def enc_step():
-        dev.encode(x, payload, total, packet=packet)
-        sharded.concat(payload, total)            # N > 1: totals scan + NVLink peer copies; N = 1: nothing
-
-    c_holder = [0]
-
-    def dec_step():
-        dev.index(payload, c_holder[0], packets, offsets, result, packet=packet)
-        dev.decode(payload, c_holder[0], offsets, packets, out, packet=packet)
-
-    def barrier():
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
         torch.cuda.synchronize()
-        if world > 1:
+        if self.world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(step, k):
+    def timed(self, step, k):
         """K steps, each bracketed by CUDA events on the launching stream, L2 flushed in between."""
+        import torch
         evs = []
         for _ in range(k):
-            flush.fill_(1)
+            self.flush.fill_(1)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             step()
@@ -333,132 +381,299 @@ def run_ours(args):
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in evs) / 1e3
 
-    # ---- warm-up (>= 3) and correctness gate: nothing is reported unless the round trip holds
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        sampler.wait_first()                      # nvidia-smi is looping from here on
-    for _ in range(max(3, args.warmup)):
-        enc_step()
-    torch.cuda.synchronize()
-    c = int(total.item())
-    c_holder[0] = c
-    for _ in range(max(3, args.warmup)):
-        dec_step()
-    # a 64 MiB step lasts ~3 ms: keep the same kernels running (untimed) for ~0.2 s so that the sampler
-    # sees the load; the count depends on the size only, so every rank does the same (enc_step is collective)
-    for _ in range(max(3, min(100, int(0.2 / (nbytes / 30e9))))):
-        enc_step()
-        dec_step()
-    torch.cuda.synchronize()
-    torch.cuda.synchronize()
-    assert [int(v) for v in result.tolist()[:3]] == [packets, nbytes, 0], result.tolist()
-    assert torch.equal(out[:nbytes], x), "decode(encode(x)) != x"
+    def all_true(self, ok):
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return bool(ok)
+        f = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        return bool(f.item())
 
-    sampler.mark()
+
+def golden_prefix(gen, seed):
+    """(bytes, md5) of the reference's payload for the head of this stream, from tests/golden/vectors.json."""
+    name = PREFIX_GOLDEN.get((gen, seed))
+    if not name:
+        return None
+    try:
+        v = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))
+        v = v["vectors"] if "vectors" in v else v
+        e = v[name] if isinstance(v, dict) else next(x for x in v if x.get("name") == name)
+        return int(e["payload_bytes"]), e["payload_md5"], name
+    except Exception:
+        return None
+
+
+def measure(rig, workload, steps, warmup, sampler=None, with_cpu_baseline=False):
+    """One workload: parity first, then the timed encode / decode / end-to-end legs.  Returns the result object."""
+    import hashlib
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from gpuar_b200 import _lib, codec
+    from gpuar_b200.shard import byte_range
+
+    args, rank, world, dev = rig.args, rig.rank, rig.world, rig.dev
+    gen, seed, nbytes, desc = WORKLOADS[workload]
+    strong = workload in STRONG
+    job = nbytes if strong else nbytes * world
+    b0, b1 = byte_range(job, rank, world) if strong else (rank * nbytes, (rank + 1) * nbytes)
+    n = b1 - b0
+    packet = args.packet if world == 1 else 8192                    # the sharded entry points speak the 8192-byte dialect
+    x = gen_device(gen, seed, b0, n)
+    packets = (n + packet - 1) // packet
+    job_packets = (job + packet - 1) // packet
+    result = torch.zeros(8, dtype=torch.int64, device="cuda")
+    if world == 1:
+        cap = codec.payload_bound(n, packet)
+        payload = torch.empty(cap + 16, dtype=torch.uint8, device="cuda")
+        total = torch.zeros(1, dtype=torch.int64, device="cuda")
+        offsets = torch.empty(packets + 1, dtype=torch.int64, device="cuda")
+        out = torch.empty(packets * packet, dtype=torch.uint8, device="cuda")
+        c_holder = [0]
+
+        def enc_step():
+            dev.encode(x, payload, total, packet=packet)
+
+        def dec_step():
+            dev.index(payload, c_holder[0], packets, offsets, result, packet=packet)
+            dev.decode(payload, c_holder[0], offsets, packets, out, packet=packet)
+    else:
+        rig.sharded.reserve(codec.payload_bound(max(n, 8192)))
+        rig.gathered.reserve(codec.payload_bound(max(n, 8192)))
+        # a rank decodes the packets that START in its segment: about job_packets / world of them
+        out = torch.empty((job_packets * 5 // (4 * world) + 64) * 8192, dtype=torch.uint8, device="cuda")
+        c_holder = [0]
+
+        def enc_step():
+            rig.sharded.encode(x)          # totals through the mailboxes, packets straight to their segment
+
+        def dec_step():
+            rig.sharded.decode(c_holder[0], out, result)
+
+    def stream_total():
+        torch.cuda.synchronize()
+        if world == 1:
+            return int(total.item()), int(total.item())
+        lay = [int(v) for v in rig.sharded.group.layout_out.tolist()[:5]]
+        assert lay[4] == 0, f"gpuar_b200_encode_sharded status {lay[4]}"
+        return lay[0], lay[3]
+
+    # ---- warm-up (>= 3) and the parity gate: nothing is reported unless it holds
+    w = max(3, warmup)
+    for _ in range(w):
+        enc_step()
+    c_all, c_mine = stream_total()
+    c_holder[0] = c_all
+    rig.barrier()                                   # the concatenated stream is complete on every GPU
+    for _ in range(w):
+        dec_step()
+    if sampler is not None:
+        # a 64 MiB step lasts ~3 ms: keep the same kernels running (untimed) for ~0.2 s so that the sampler
+        # sees the load; the count depends on the size only, so every rank does the same (the steps are collective)
+        for _ in range(max(3, min(100, int(0.2 / (n / 30e9))))):
+            enc_step()
+            dec_step()
+    torch.cuda.synchronize()
+    parity = {}
+    if world == 1:
+        res = [int(v) for v in result.tolist()[:3]]
+        parity["round_trip"] = res == [packets, n, 0] and bool(torch.equal(out[:n], x))
+        head = payload
+    else:
+        mine, raw, status, before, raw_before = (int(v) for v in result.tolist()[:5])
+        ok = status == 0 and raw_before == min(before * 8192, job) and equals_stream(gen, seed, raw_before, out[:raw])
+        counts = torch.tensor([mine, raw], dtype=torch.int64, device="cuda")
+        dist.all_reduce(counts)
+        covered = [int(v) for v in counts.tolist()] == [job_packets, job]
+        # every rank's decoded slice of the CONCATENATED stream equals the input, and the slices cover the job
+        parity["concat_round_trip"] = rig.all_true(ok and covered)
+        # the whole stream gathered onto rank 0 and decoded there by the single-GPU path
+        for _ in range(2):
+            rig.gathered.encode(x)
+        rig.barrier()
+        good = True
+        head = None
+        if rank == 0:
+            view, valid = rig.gathered.group.my_segment()
+            head = view
+            good = valid == c_all
+            if good:
+                padded = torch.as_tensor(rig.gathered.group.segment_view(valid + 64))
+                padded[valid:] = 0
+                offs, res = dev.index(padded, valid, job_packets)
+                full = dev.decode(padded, valid, offs, job_packets)
+                torch.cuda.synchronize()
+                good = [int(v) for v in res.tolist()[:3]] == [job_packets, job, 0] and equals_stream(gen, seed, 0, full[:job])
+                del full, offs
+        parity["gathered_round_trip_on_rank0"] = rig.all_true(good)
+    gp = golden_prefix(gen, seed) if packet == 8192 else None
+    if gp and rank == 0 and c_all >= gp[0]:
+        got = hashlib.md5(head[: gp[0]].cpu().numpy().tobytes()).hexdigest()
+        parity["prefix_md5"] = got == gp[1]
+        parity["prefix_md5_of"] = f"first {gp[0]} stream bytes == the reference's payload for the first " \
+                                  f"{'64 MiB' if gp[2] == 'u64m' else '1 MiB'} of this input (tests/golden {gp[2]})"
+    flags = [v for k, v in parity.items() if isinstance(v, bool)]
+    assert rig.all_true(all(flags)), f"parity failed on rank {rank}: {parity}"
+    head = None
+
+    if sampler is not None:
+        sampler.mark()
     launches0 = _lib.launch_count()
     _lib.profile(True)
     _lib.profile_read()
-    barrier()
-    t_enc = timed(enc_step, args.steps)
-    barrier()
-    t_local = timed(lambda: dev.encode(x, payload, total, packet=packet), args.steps) if world > 1 else t_enc
-    barrier()
-
-    def gather_step():
-        dev.encode(x, payload, total, packet=packet)
-        gathered.concat(payload, total)
-
-    t_gather = t_enc
-    if gathered:
-        for _ in range(3):
+    rig.barrier()
+    t_enc = rig.timed(enc_step, steps)
+    rig.barrier()
+    t_local = t_gather = t_enc
+    if world > 1:
+        payload = torch.empty(codec.payload_bound(n) + 16, dtype=torch.uint8, device="cuda")
+        total = torch.zeros(1, dtype=torch.int64, device="cuda")
+        local_step = lambda: dev.encode(x, payload, total)
+        for _ in range(2):
+            local_step()
+        rig.barrier()
+        t_local = rig.timed(local_step, steps)
+        del payload
+        rig.barrier()
+        gather_step = lambda: rig.gathered.encode(x)
+        for _ in range(2):
             gather_step()
-        barrier()
-        t_gather = timed(gather_step, args.steps)
-        barrier()
-    t_dec = timed(dec_step, args.steps)
-    barrier()
+        rig.barrier()
+        t_gather = rig.timed(gather_step, steps)
+        rig.barrier()
+        for _ in range(2):                         # the stream the decode reads: back to the segments layout
+            enc_step()
+        rig.barrier()
+    t_dec = rig.timed(dec_step, steps)
+    rig.barrier()
     spans = _lib.profile_read()
     _lib.profile(False)
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e through the host-buffer entry points, pinned host memory
-    host_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    # ---- e2e through the host-buffer entry points, pinned host memory (every rank its own shard)
+    if world > 1:
+        del out
+        out = None
+    host_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     host_in.copy_(x)
-    host_gip = torch.empty(20 + codec.payload_bound(nbytes), dtype=torch.uint8).pin_memory()   # e2e: 8192-byte packets
-    host_out = torch.empty(nbytes + 8192, dtype=torch.uint8).pin_memory()
+    host_gip = torch.empty(20 + codec.payload_bound(n), dtype=torch.uint8, pin_memory=True)   # e2e: 8192-byte packets
+    host_out = torch.empty(n + 8192, dtype=torch.uint8, pin_memory=True)
     np_in, np_gip, np_out = host_in.numpy(), host_gip.numpy(), host_out.numpy()
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(steps, 3 if n >= (1 << 30) else 5))
     g = codec.compress(np_in, out=np_gip)
     codec.decompress(g, out=np_out)
-    barrier()
+    rig.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         g = codec.compress(np_in, out=np_gip)
     torch.cuda.synchronize()
     t_e2e_enc = (time.perf_counter() - t0) / e2e_steps
-    barrier()
+    rig.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         back = codec.decompress(g, out=np_out)
     torch.cuda.synchronize()
     t_e2e_dec = (time.perf_counter() - t0) / e2e_steps
-    assert back.size == nbytes and np.array_equal(back[:4096], np_in[:4096]) and np.array_equal(back[-4096:], np_in[-4096:])
+    assert back.size == n and np.array_equal(back[:4096], np_in[:4096]) and np.array_equal(back[-4096:], np_in[-4096:])
     gip_bytes = int(g.size)
+    del host_in, host_gip, host_out, np_in, np_gip, np_out, g, back
 
-    # ---- max over ranks
-    times = torch.tensor([t_enc, t_dec, t_e2e_enc, t_e2e_dec, t_local, t_gather], dtype=torch.float64, device="cuda")
+    # ---- max over ranks (per-step seconds)
+    times = torch.tensor([t_enc / steps, t_dec / steps, t_e2e_enc, t_e2e_dec, t_local / steps, t_gather / steps],
+                         dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     t_enc, t_dec, t_e2e_enc, t_e2e_dec, t_local, t_gather = (float(v) for v in times.tolist())
 
+    res = None
     if rank == 0:
-        job = nbytes * world
         peak, peak_src = measured_peaks()
-        enc_ms, enc_calls = spans["encode"]
-        alg_bytes = nbytes + c                                     # N read + C written per launch
-        achieved = alg_bytes / (enc_ms / 1e3 / max(1, enc_calls)) / GB
-        line = {
-            "metric": "encode_GBps", "value": job / (t_enc / args.steps) / GB, "unit": "GB/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": t_enc / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": desc, "bytes_per_rank": nbytes, "packet_bytes": packet,
-                       "payload_bytes_rank0": c, "l2": "flushed between timed iterations (256 MiB write)",
-                       "parallelism": f"packet-range shards x{world}" if world > 1 else "single GPU",
-                       "encode_path": args.encode_path, "work_unit_packets": args.work_unit or "auto"},
-            "encode_shards_in_place": {"value": job / (t_local / args.steps) / GB, "unit": "GB/s",
-                                       "note": "encode only, every shard's payload left on its own GPU (SURVEY 8e)"},
-            "encode_gather_one_gpu": {"value": job / (t_gather / args.steps) / GB, "unit": "GB/s",
-                                      "note": "concatenation of the whole stream into rank 0's memory: ingress-limited "
-                                              "on that GPU (SURVEY 8e); `value` concatenates into W equal segments, "
-                                              "segment g on GPU g, so every GPU receives total/W bytes"},
-            "decode": {"value": job / (t_dec / args.steps) / GB, "unit": "GB/s",
-                       "ms_per_step": t_dec / args.steps * 1e3,
-                       "includes": "device packet-chain discovery + decode kernel"},
-            "e2e": {"value": job / t_e2e_enc / GB, "unit": "GB/s", "h2d_bytes_per_step": nbytes,
-                    "d2h_bytes_per_step": gip_bytes - 20, "api": "gpuar_b200_compress_host (pinned host buffers)"},
+        per = lambda k: spans[k][0] / max(1, spans[k][1])                       # ms per launch group
+        alg = n + c_mine                                                        # SURVEY 8(d): N read + C written per launch
+        enc_traffic, enc_note = measured_traffic(workload, "encode")
+        dec_traffic, _ = measured_traffic(workload, "decode")
+        res = {
+            "workload": workload, "desc": desc, "scaling": "strong" if strong else "weak", "job_bytes": job,
+            "bytes_rank0": n, "payload_bytes": c_all, "payload_bytes_rank0": c_mine,
+            "value": job / t_enc / GB, "unit": "GB/s", "ms_per_step": t_enc * 1e3,
+            "decode": {"value": job / t_dec / GB, "unit": "GB/s", "ms_per_step": t_dec * 1e3,
+                       "includes": "device packet-chain discovery + decode kernel" +
+                                   (" (every rank: its own segment of the concatenated stream)" if world > 1 else "")},
+            "e2e": {"value": job / t_e2e_enc / GB, "unit": "GB/s", "h2d_bytes_per_step": n,
+                    "d2h_bytes_per_step": gip_bytes - 20, "api": "gpuar_b200_compress_host (pinned host buffers)" +
+                    (", every rank its own shard" if world > 1 else "")},
             "e2e_decode": {"value": job / t_e2e_dec / GB, "unit": "GB/s", "h2d_bytes_per_step": gip_bytes - 20,
-                           "d2h_bytes_per_step": nbytes, "api": "gpuar_b200_decompress_host"},
+                           "d2h_bytes_per_step": n, "api": "gpuar_b200_decompress_host"},
+            "parity": parity,
             "gpu_launches": launches,
-            "kernels_ms_per_step": {k: (v[0] / max(1, v[1])) for k, v in spans.items()},
-            "roofline": {"bound": "hbm", "kernel": "encode kernel (encode_ws_kernel up to one wave, else encode_kernel)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(args.workload, "encode"), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes,
+            "kernels_ms_per_step": {k: per(k) for k in spans},
+            "roofline": {"bound": "hbm", "kernel": "encode kernel (encode_ws_kernel up to two waves of its CTAs, else encode_kernel)",
+                         "achieved": alg / (per("encode") / 1e3) / GB, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (per("encode") / 1e3) / GB / peak, "traffic": enc_traffic, "traffic_source": enc_note,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "note": "integer-latency-bound path: see profiles/ for issue-slot and occupancy evidence"},
             "roofline_decode": {"bound": "hbm", "kernel": "decode_kernel",
-                                "achieved": alg_bytes / (spans["decode"][0] / 1e3 / max(1, spans["decode"][1])) / GB,
-                                "peak": peak, "unit": "GB/s",
-                                "frac": alg_bytes / (spans["decode"][0] / 1e3 / max(1, spans["decode"][1])) / GB / peak,
-                                "traffic": measured_traffic(args.workload, "decode"),
-                                "algorithmic_bytes_per_launch": alg_bytes},
-            "clocks": clocks,
+                                "achieved": alg / (per("decode") / 1e3) / GB, "peak": peak, "unit": "GB/s",
+                                "frac": alg / (per("decode") / 1e3) / GB / peak, "traffic": dec_traffic,
+                                "algorithmic_bytes_per_launch": alg},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            base, _ = cpu_baseline(args.workload)
-            line["cpu_baseline"] = base
+        if world > 1:
+            res["encode_shards_in_place"] = {"value": job / t_local / GB, "unit": "GB/s",
+                                             "note": "encode only, every shard's payload left on its own GPU (SURVEY 8e)"}
+            res["encode_gather_one_gpu"] = {"value": job / t_gather / GB, "unit": "GB/s",
+                                            "note": "the whole stream written into rank 0's memory: ingress-limited on that "
+                                                    "GPU (SURVEY 8e); `value` writes W equal segments, segment g on GPU g"}
+            res["exchange"] = "per-rank totals through peer-mapped mailboxes, packets stored straight into the " \
+                              "segments over NVLink; no NCCL call and no host round trip in the timed region"
+        if with_cpu_baseline:
+            base, sample, ref_pay = cpu_baseline(workload)
+            res["cpu_baseline"] = base
+            if packet == 8192 and base["kind"] == "reference":
+                # the head of our stream against the reference's own output for the same bytes
+                k = min(int(ref_pay.size), c_all)
+                src = payload if world == 1 else None
+                if src is not None:
+                    res["parity"]["head_equals_reference_cpu_output"] = bool(
+                        np.array_equal(src[:k].cpu().numpy(), ref_pay[:k]))
+                    res["parity"]["head_bytes_compared"] = k
+                    assert res["parity"]["head_equals_reference_cpu_output"], "payload differs from the reference's"
+    return res
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rig = Rig(args)
+    rank, world = rig.rank, rig.world
+    sampler = ClockSampler(rig.local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first()                      # nvidia-smi is looping from here on
+    main = measure(rig, args.workload, args.steps, args.warmup, sampler=sampler,
+                   with_cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+    clocks = sampler.stop() if rank == 0 else None
+    subs = {}
+    for name in [w for w in args.sub.split(",") if w and w != args.workload]:
+        torch.cuda.empty_cache()
+        subs[name] = measure(rig, name, args.steps, args.warmup)
+    if rank == 0:
+        line = {
+            "metric": "encode_GBps", "value": main["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": main["scaling"], "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+            "config": job_config(args, world),
+        }
+        for k in ("decode", "e2e", "e2e_decode", "parity", "roofline", "roofline_decode", "kernels_ms_per_step",
+                  "encode_shards_in_place", "encode_gather_one_gpu", "exchange", "cpu_baseline", "payload_bytes",
+                  "bytes_rank0", "payload_bytes_rank0"):
+            if k in main:
+                line[k] = main[k]
+        line["gpu_launches"] = main["gpu_launches"] + sum(v["gpu_launches"] for v in subs.values())
+        line["clocks"] = clocks
+        line["sub"] = subs
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -471,7 +686,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="u64m", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="m16g", choices=sorted(WORKLOADS))
+    ap.add_argument("--sub", default="u64m,s1g",
+                    help="comma-separated workloads measured after the main one and reported under \"sub\" ('' = none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--packet", type=int, default=8192,
                     help="raw bytes per packet for the device-resident numbers (8192 = the reference format; "

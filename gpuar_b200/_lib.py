@@ -56,7 +56,11 @@ SIGNATURES = {
     "gpuar_b200_write_header": (None, [_vp, C.c_uint64, C.c_uint64]),
     "gpuar_b200_check_header": (C.c_int, [_vp]),
     "gpuar_b200_peer_concat": (C.c_int, [_vp, C.c_int, _sz, _vp, C.c_int, _sz, _vp]),
-    "gpuar_b200_shard_concat": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp), C.c_int, _sz, _vp, _vp]),
+    "gpuar_b200_encode_sharded": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
+    "gpuar_b200_shard_segment_bytes": (C.c_uint64, [C.c_uint64, C.c_int]),
+    "gpuar_b200_decode_sharded_scratch_bytes": (_sz, [C.c_uint64, _sz]),
+    "gpuar_b200_decode_sharded": (C.c_int, [_vp, C.c_uint64, _vp, _sz, _vp, _vp, _sz, _vp]),
+    "gpuar_b200_enable_peer": (C.c_int, [C.c_int]),
     "gpuar_b200_device_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
     "gpuar_b200_device_free": (C.c_int, [_vp]),
     "gpuar_b200_host_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
@@ -74,6 +78,17 @@ SIGNATURES = {
     "gpuar_b200_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "gpuar_b200_launch_count": (C.c_uint64, []),
 }
+
+MAX_RANKS = 16            # GPUAR_MAX_RANKS
+MAILBOX_BYTES = 1024      # GPUAR_MAILBOX_BYTES
+
+
+class Shard(C.Structure):
+    """gpuar_b200_shard (include/gpuar_b200.h)."""
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("n_segments", C.c_int32), ("reserved", C.c_int32),
+                ("seg_cap", C.c_uint64), ("segments", _vp * MAX_RANKS), ("mailbox", _vp * MAX_RANKS),
+                ("calls", C.c_uint64 * 4)]
+
 
 _lib = None
 

@@ -650,16 +650,106 @@ int gpuar_b200_peer_concat(uint8_t *d_dst, int dst_device, size_t dst_offset, co
     return ck(cudaMemcpyPeerAsync(d_dst + dst_offset, dst_device, d_src, src_device, bytes, (cudaStream_t)stream));
 }
 
-int gpuar_b200_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, int rank, int world,
-                            uint8_t *const *segments, int n_segments, size_t seg_cap, uint64_t *d_layout, void *stream)
+static bool shard_ok(const gpuar_b200_shard *sh)
 {
-    if (!d_payload || !d_totals || !segments || rank < 0 || rank >= world || world > 16) return GPUAR_E_ARG;
-    if (n_segments < 1 || n_segments > 16) return GPUAR_E_ARG;
-    if ((uintptr_t)d_payload & 15u) return GPUAR_E_ARG;
-    for (int g = 0; g < n_segments; ++g)
-        if (!segments[g]) return GPUAR_E_ARG;
-    return ck(launch_shard_concat(d_payload, d_totals, (uint32_t)rank, (uint32_t)world, segments, (uint32_t)n_segments,
-                                  seg_cap, d_layout, (cudaStream_t)stream));
+    if (!sh || sh->world < 1 || sh->world > GPUAR_MAX_RANKS || sh->rank < 0 || sh->rank >= sh->world) return false;
+    if (sh->n_segments != 1 && sh->n_segments != sh->world) return false;
+    for (int g = 0; g < sh->n_segments; ++g)
+        if (!sh->segments[g] || ((uintptr_t)sh->segments[g] & 15u)) return false;
+    for (int r = 0; r < sh->world; ++r)
+        if (!sh->mailbox[r] || ((uintptr_t)sh->mailbox[r] & 7u)) return false;
+    return true;
+}
+
+static ShardPlace shard_place(const gpuar_b200_shard *sh)
+{
+    ShardPlace w{};
+    for (int g = 0; g < sh->n_segments; ++g) w.segment[g] = sh->segments[g];
+    for (int r = 0; r < sh->world; ++r) w.mailbox[r] = sh->mailbox[r];
+    w.seg_cap = sh->seg_cap;
+    w.rank = (uint32_t)sh->rank;
+    w.world = (uint32_t)sh->world;
+    w.n_segments = (uint32_t)sh->n_segments;
+    return w;
+}
+
+int gpuar_b200_encode_sharded(gpuar_b200_shard *shard, const uint8_t *d_in, size_t n, uint64_t *d_layout,
+                              uint32_t *d_packet_sizes, void *d_scratch, size_t scratch_bytes, void *stream)
+{
+    if (!shard_ok(shard) || !d_layout || !d_scratch || (n && !d_in)) return GPUAR_E_ARG;
+    if (((uintptr_t)d_in | (uintptr_t)d_scratch) & 15u) return GPUAR_E_ARG;
+    const EncodePlan p = encode_plan(n);
+    if (scratch_bytes < p.total || p.packets > 0xFFFFFFF0ull) return GPUAR_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *s = static_cast<uint8_t *>(d_scratch);
+    uint32_t *sizes = d_packet_sizes ? d_packet_sizes : reinterpret_cast<uint32_t *>(s + p.off_sizes);
+    cudaError_t e;
+    {
+        Scope t(GPUAR_SPAN_ENCODE, st);
+        e = encode_slots(d_in, n, s + p.off_slots, kSlot, sizes, kPacket, st);
+    }
+    if (e != cudaSuccess) return ck(e);
+    const uint64_t call = shard->calls[0]++;
+    Scope t(GPUAR_SPAN_COMPACT, st);
+    return ck(launch_compact_sharded(s + p.off_slots, kSlot, sizes, (uint32_t)p.packets,
+                                     reinterpret_cast<uint64_t *>(s + p.off_desc), d_layout, shard_place(shard), call, st));
+}
+
+uint64_t gpuar_b200_shard_segment_bytes(uint64_t stream_bytes, int n_segments)
+{
+    if (n_segments < 1) return 0;
+    const uint64_t seg = ((stream_bytes + (uint64_t)n_segments - 1) / (uint64_t)n_segments + 255) & ~(uint64_t)255;
+    return seg ? seg : 256;                          /* what the compaction kernel computes (shard_segment_bytes) */
+}
+
+/* sharded decode scratch: [offsets: max_packets * 8][index scratch of one segment] */
+size_t gpuar_b200_decode_sharded_scratch_bytes(uint64_t seg_bytes, size_t max_packets)
+{
+    return align_up(max_packets * 8 + 8, 256) + index_scratch_bytes((size_t)seg_bytes);
+}
+
+int gpuar_b200_decode_sharded(gpuar_b200_shard *shard, uint64_t stream_bytes, uint8_t *d_out, size_t out_cap,
+                              uint64_t *d_result, void *d_scratch, size_t scratch_bytes, void *stream)
+{
+    if (!shard_ok(shard) || shard->n_segments != shard->world || !d_result || !d_scratch) return GPUAR_E_ARG;
+    if (((uintptr_t)d_out | (uintptr_t)d_scratch) & 15u) return GPUAR_E_ARG;
+    const uint64_t seg = gpuar_b200_shard_segment_bytes(stream_bytes, shard->world);
+    const size_t max_packets = out_cap / kPacket;
+    if (seg > shard->seg_cap || max_packets > 0xFFFFFFF0ull || (max_packets && !d_out)) return GPUAR_E_ARG;
+    if (scratch_bytes < gpuar_b200_decode_sharded_scratch_bytes(seg, max_packets)) return GPUAR_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *s = static_cast<uint8_t *>(d_scratch);
+    uint64_t *offsets = reinterpret_cast<uint64_t *>(s);
+    const size_t off_index = align_up(max_packets * 8 + 8, 256);
+    const ShardPlace where = shard_place(shard);
+    const uint64_t call = shard->calls[1]++;
+    cudaError_t e = cudaMemsetAsync(d_result, 0, 8 * sizeof(uint64_t), st);
+    if (e != cudaSuccess) return ck(e);
+    {
+        Scope t(GPUAR_SPAN_INDEX, st);
+        e = launch_index_segment(where, call, stream_bytes, seg, offsets, max_packets, d_result, s + off_index,
+                                 scratch_bytes - off_index, st);
+    }
+    if (e != cudaSuccess || !max_packets) return ck(e);
+    const uint64_t base = seg * (uint64_t)shard->rank;
+    const uint64_t here = base < stream_bytes ? (stream_bytes - base < seg ? stream_bytes - base : seg) : 0;
+    Scope t(GPUAR_SPAN_DECODE, st);
+    return ck(launch_decode(shard->segments[shard->rank], (size_t)here + (base + seg < stream_bytes ? kShardHalo : 64u),
+                            offsets, 0, (uint32_t)max_packets, d_out, kPacket, st, d_result));
+}
+
+int gpuar_b200_enable_peer(int peer_device)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return ck(e);
+    if (dev == peer_device) return 0;
+    int can = 0;
+    if ((e = cudaDeviceCanAccessPeer(&can, dev, peer_device)) != cudaSuccess) return ck(e);
+    if (!can) return GPUAR_E_UNSUPPORTED;
+    e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    return ck(e);
 }
 
 int gpuar_b200_device_alloc(size_t bytes, void **d_ptr)
@@ -673,7 +763,7 @@ int gpuar_b200_device_free(void *d_ptr) { return ck(cudaFree(d_ptr)); }
 int gpuar_b200_host_alloc(size_t bytes, void **h_ptr)
 {
     if (!h_ptr) return GPUAR_E_ARG;
-    return ck(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return ck(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocPortable));   // usable from every device's context
 }
 
 int gpuar_b200_host_free(void *h_ptr) { return ck(cudaFreeHost(h_ptr)); }

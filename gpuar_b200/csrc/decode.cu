@@ -64,11 +64,16 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <bool kRingFeed>
 __global__ void __launch_bounds__(32)
 decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64_t *__restrict__ offsets,
-              uint32_t stride, uint32_t n_packets, uint8_t *__restrict__ out, uint32_t packet)
+              uint32_t stride, uint32_t n_packets, uint8_t *__restrict__ out, uint32_t packet,
+              const uint64_t *__restrict__ count)
 {
     __shared__ __align__(16) DecShared<kRingFeed> sm;
     const uint32_t lane = lane_id();
     const uint32_t my = blockIdx.x * 32u + lane;
+    if (count) {                                    // sharded decode: the chain discovery left the count on the device
+        n_packets = (uint32_t)min((uint64_t)n_packets, *count);
+        if (blockIdx.x * 32u >= n_packets) return;
+    }
     const bool mine = my < n_packets;
 
     // model init: every count 1 (gpuar_kernel.cu:403-419)
@@ -197,7 +202,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
 }
 
 cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint64_t *d_offsets, uint32_t stride,
-                          uint32_t packets, uint8_t *d_out, uint32_t packet, cudaStream_t st)
+                          uint32_t packets, uint8_t *d_out, uint32_t packet, cudaStream_t st, const uint64_t *d_count)
 {
     if (!packets) return cudaSuccess;
     int dev = 0, sms = 148;
@@ -212,9 +217,9 @@ cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint6
     // 4.41 against 3.30 ms at 368 MiB; profiles/r1_s2_dec_switch.txt).
     const uint32_t ring_max = forced >= 0 ? (uint32_t)forced : (uint32_t)sms * 4u;
     if (grid <= ring_max)
-        decode_kernel<true><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet);
+        decode_kernel<true><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet, d_count);
     else
-        decode_kernel<false><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet);
+        decode_kernel<false><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet, d_count);
     count_launch();
     return cudaGetLastError();
 }

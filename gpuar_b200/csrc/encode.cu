@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "lookback.cuh"
+#include "shard.cuh"
 
 namespace gpuar {
 
@@ -220,25 +221,111 @@ __device__ __forceinline__ void warp_copy_any(uint8_t *__restrict__ dst, const u
     }
 }
 
+// ------------------------------------------------- multi-GPU: where a rank's stream lands
+// The ranks' streams are concatenated in rank (= packet) order: rank r's stream starts at the
+// exclusive scan of the W per-rank totals.  The concatenated stream lives in n_segments equal
+// SEGMENTS of S = ceil(total / n_segments) bytes (rounded up to 256), segment g on GPU g: global
+// offset o is byte o % S of segment o / S.  With balanced shards almost every byte stays on its
+// own GPU and only the spill-over crosses NVLink; with skewed shards every GPU still receives
+// exactly S bytes, so no GPU's ingress is the bottleneck.  One segment of the whole capacity is
+// the gather-onto-one-GPU layout (ingress-limited there).  The segment pointers are local or
+// peer-mapped (cudaIpcOpenMemHandle / cudaDeviceEnablePeerAccess); stores are 16 bytes wide.
+//
+// The only exchange between the ranks is the W totals.  They travel through MAILBOXES: every
+// rank owns a small block of device memory that all ranks can write (peer-mapped); after its
+// encode kernel a rank reduces its packet sizes and stores `tag | total` into word
+// [parity][rank] of EVERY rank's mailbox (shard_total_kernel), and the compaction kernel of a
+// rank reads the W words of its OWN mailbox, spinning until they carry the tag of this call.
+// No host round trip, no NCCL, and the compaction writes each packet straight to its final
+// place: there is no second pass over the payload.
+//   tag    = call counter modulo 2^20 - 1, plus 1 (0 = never written), in bits 44..63
+//   parity = call counter & 1: a rank can be at most one call ahead of the slowest one (it needs
+//            that rank's total of call e+1, which is stream-ordered after its compaction of call
+//            e), so two buffers suffice.
+// Sum of this rank's packet sizes -> `tag | total` into every rank's mailbox.  `acc` = u64[2]
+// scratch (sum, CTAs done), zeroed by the launcher.
+__global__ void __launch_bounds__(256)
+shard_total_kernel(const uint32_t *__restrict__ sizes, uint32_t n_packets, uint64_t *__restrict__ acc, ShardTarget tg)
+{
+    uint64_t sum = 0;
+    for (size_t i = (size_t)blockIdx.x * 256u + threadIdx.x; i < n_packets; i += (size_t)gridDim.x * 256u) sum += sizes[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+    __shared__ uint64_t s_part[8];
+    if (lane_id() == 0) s_part[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x) return;
+    for (int w = 1; w < 8; ++w) sum += s_part[w];
+    atomicAdd(reinterpret_cast<unsigned long long *>(&acc[0]), (unsigned long long)sum);
+    __threadfence();
+    if (atomicAdd(reinterpret_cast<unsigned long long *>(&acc[1]), 1ull) + 1ull != gridDim.x) return;
+    __threadfence();
+    const uint64_t total = ld_desc(&acc[0]);
+    const uint64_t word = ((uint64_t)tg.tag << kTagShift) | (total & kValueMask);
+    for (uint32_t r = 0; r < tg.world; ++r) st_sys(tg.mailbox[r] + kMailTotals + tg.parity * kMaxRanks + tg.rank, word);
+    __threadfence_system();
+}
+
+// Called by one full warp: the W totals of this call from the rank's own mailbox.  Returns false
+// on a timeout.  base = bytes of the ranks before this one, all = bytes of all ranks.
+__device__ __forceinline__ bool shard_totals(const ShardTarget &tg, uint32_t lane, uint64_t &base, uint64_t &all,
+                                             uint64_t &mine)
+{
+    uint64_t v = 0;
+    bool ok = true;
+    if (lane < tg.world) {
+        const uint64_t *p = tg.mailbox[tg.rank] + kMailTotals + tg.parity * kMaxRanks + lane;
+        const uint64_t t0 = global_ns();
+        for (;;) {
+            v = ld_sys(p);
+            if ((uint32_t)(v >> kTagShift) == tg.tag) break;
+            if (global_ns() - t0 > kMailTimeoutNs) { ok = false; break; }
+            __nanosleep(64);
+        }
+        v &= kValueMask;
+    }
+    ok = __all_sync(kFull, ok);
+    uint64_t b = lane < tg.rank ? v : 0ull, a = v;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        b += __shfl_xor_sync(kFull, b, o);
+        a += __shfl_xor_sync(kFull, a, o);
+    }
+    base = b;
+    all = a;
+    mine = __shfl_sync(kFull, v, (int)tg.rank);
+    return ok;
+}
+
+__device__ __forceinline__ uint64_t shard_segment_bytes(const ShardTarget &tg, uint64_t all)
+{
+    if (tg.n_segments <= 1) return tg.seg_cap;
+    const uint64_t seg = ((all + tg.n_segments - 1) / tg.n_segments + 255) & ~(uint64_t)255;
+    return seg ? seg : 256;
+}
+
 // kGuard: the destination holds `cap` bytes and the sizes come from an untrusted stream (the
 // rawLen fields of a foreign .gip, decode side): a packet that would end past `cap` is not
 // copied; *total_out still reports the full sum, so the caller sees that it did not fit.
-template <bool kGuard>
+// kSharded: the destination is the concatenated stream of all ranks (ShardTarget); `total_out`
+// = u64[5]: bytes of all ranks, segment size, this rank's base offset, this rank's bytes, status
+// (0 ok, 1 a segment is too small, 2 a peer's total never arrived).
+template <bool kGuard, bool kSharded>
 __global__ void __launch_bounds__(kCompactThreads)
 compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const uint32_t *__restrict__ sizes,
                uint32_t n_packets, uint32_t tile_packets, uint8_t *__restrict__ payload, uint64_t *__restrict__ desc,
-               uint32_t *__restrict__ ticket, uint64_t *__restrict__ total_out, uint64_t cap)
+               uint32_t *__restrict__ ticket, uint64_t *__restrict__ total_out, uint64_t cap, ShardTarget tg)
 {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_off[kMaxTilePackets + 1];
-    __shared__ uint64_t s_base;
+    __shared__ uint64_t s_base, s_seg;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
 
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);          // tiles start in ticket order
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t first = tile * tile_packets;
-    const uint32_t count = min(tile_packets, n_packets - first);
+    const uint32_t count = first < n_packets ? min(tile_packets, n_packets - first) : 0u;
 
     if (warp == 0) {
         // exclusive scan of this tile's sizes (four per lane)
@@ -264,72 +351,50 @@ compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const ui
         if (lane == 0) s_off[kMaxTilePackets] = total;              // entry 4*lane+i == count already holds it when count < 128
 
         // decoupled look-back for the bytes that precede this tile
-        const uint64_t base = lookback_exclusive(desc, tile, total, lane);
+        uint64_t base = lookback_exclusive(desc, tile, total, lane);
+        uint64_t seg = 0;
+        if (kSharded) {
+            uint64_t rank_base, all, mine;
+            const bool ok = shard_totals(tg, lane, rank_base, all, mine);
+            seg = shard_segment_bytes(tg, all);
+            const uint64_t status = !ok ? 2ull : (seg > tg.seg_cap || (tg.n_segments <= 1 && all > seg)) ? 1ull : 0ull;
+            if (status) seg = 0;                                    // nothing is copied
+            base += rank_base;
+            if (lane == 0 && first + count >= n_packets) {
+                total_out[0] = all;
+                total_out[1] = status ? 0 : seg;
+                total_out[2] = rank_base;
+                total_out[3] = mine;
+                total_out[4] = status;
+            }
+        } else if (lane == 0 && first + count == n_packets) {
+            *total_out = base + total;
+        }
         if (lane == 0) {
             s_base = base;
-            if (first + count == n_packets) *total_out = base + total;
+            s_seg = seg;
         }
     }
     __syncthreads();
 
     const uint64_t base = s_base;
-    for (uint32_t q = warp; q < count; q += kCompactThreads / 32u) {
-        if (kGuard && base + s_off[q + 1u] > cap) continue;
-        warp_copy_unaligned(payload + base + s_off[q], slots + (size_t)(first + q) * slot_stride,
-                            s_off[q + 1u] - s_off[q], lane);
-    }
-}
-
-// ------------------------------------------------- multi-GPU stream concatenation
-// The ranks' payloads are concatenated in rank (= packet) order: rank r's stream starts at the
-// exclusive scan of the W payload totals.  The concatenated stream lives in W equal SEGMENTS of
-// S = ceil(total / W) bytes (rounded up to 256), segment g on GPU g: global offset o is byte
-// o % S of segment o / S.  With balanced shards almost every byte stays on its own GPU and only
-// the spill-over crosses NVLink; with skewed shards every GPU still receives exactly S bytes, so
-// no GPU's ingress is the bottleneck (gathering everything onto one GPU is ingress-limited to
-// one link set).  `segments` holds the device pointers, local or peer-mapped (cudaIpcOpenMemHandle);
-// a single segment of the whole capacity reproduces the gather-to-one-GPU layout.  The totals
-// are read from device memory, so the host never waits for a size; stores are 16 bytes wide.
-constexpr uint32_t kConcatThreads = 256;
-constexpr uint32_t kConcatPiece = 4096;             // bytes per warp-iteration (16-byte aligned source)
-
-struct SegmentList { uint8_t *base[16]; };
-
-__global__ void __launch_bounds__(kConcatThreads)
-shard_concat_kernel(const uint8_t *__restrict__ payload, const uint64_t *__restrict__ totals, uint32_t rank,
-                    uint32_t world, SegmentList segments, uint32_t n_segments, uint64_t seg_cap,
-                    uint64_t *__restrict__ layout_out)
-{
-    uint64_t base = 0, all = 0;
-    for (uint32_t r = 0; r < world; ++r) {
-        const uint64_t t = totals[r];
-        if (r < rank) base += t;
-        all += t;
-    }
-    const uint64_t bytes = totals[rank];
-    // segment size: equal split of the whole stream, 256-byte granules; one segment = plain gather
-    uint64_t seg = n_segments > 1 ? (((all + n_segments - 1) / n_segments + 255) & ~(uint64_t)255) : seg_cap;
-    if (seg == 0) seg = 256;
-    if (seg > seg_cap) return;                       // never write past a destination (caller sized it too small)
-    if (layout_out && blockIdx.x == 0 && threadIdx.x == 0) {
-        layout_out[0] = all;
-        layout_out[1] = seg;
-        layout_out[2] = base;
-    }
-    const uint32_t lane = lane_id();
-    const uint64_t warps = (uint64_t)gridDim.x * (kConcatThreads / 32u);
-    const uint64_t w = (uint64_t)blockIdx.x * (kConcatThreads / 32u) + (threadIdx.x >> 5);
-    for (uint64_t at = w * kConcatPiece; at < bytes; at += warps * kConcatPiece) {
-        uint32_t len = (uint32_t)min((uint64_t)kConcatPiece, bytes - at);
-        uint64_t o = base + at;                      // global offset of this piece
-        const uint8_t *src = payload + at;
-        while (len) {                                // a piece may straddle a segment boundary
+    if (kSharded) {
+        const uint64_t seg = s_seg;
+        if (seg == 0) return;
+        for (uint32_t q = warp; q < count; q += kCompactThreads / 32u) {
+            const uint64_t o = base + s_off[q];
+            const uint32_t len = s_off[q + 1u] - s_off[q];
             const uint64_t g = o / seg, in = o - g * seg;
-            const uint32_t part = (uint32_t)min((uint64_t)len, seg - in);
-            if (g < n_segments) warp_copy_any(segments.base[g] + in, src, part, lane);
-            o += part;
-            src += part;
-            len -= part;
+            const uint8_t *src = slots + (size_t)(first + q) * slot_stride;
+            const uint32_t head = (uint32_t)min((uint64_t)len, seg - in);
+            warp_copy_unaligned(tg.segment[g] + in, src, head, lane);
+            if (head < len) warp_copy_any(tg.segment[g + 1u], src + head, len - head, lane);   // straddles a boundary
+        }
+    } else {
+        for (uint32_t q = warp; q < count; q += kCompactThreads / 32u) {
+            if (kGuard && base + s_off[q + 1u] > cap) continue;
+            warp_copy_unaligned(payload + base + s_off[q], slots + (size_t)(first + q) * slot_stride,
+                                s_off[q + 1u] - s_off[q], lane);
         }
     }
 }
@@ -370,7 +435,7 @@ static uint32_t compact_tile_for(size_t packets)
 size_t compact_desc_bytes(size_t packets)
 {
     const size_t tiles = (packets + 3) / 4;                         // the smallest tile there is
-    return (tiles + 2) * sizeof(uint64_t);                          // descriptors + ticket word
+    return (tiles + 5) * sizeof(uint64_t);                          // descriptors + ticket word + totals accumulator
 }
 
 cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const uint32_t *d_sizes,
@@ -383,29 +448,49 @@ cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const u
     if (e != cudaSuccess) return e;
     if (!packets) return cudaMemsetAsync(d_total, 0, sizeof(uint64_t), st);
     uint32_t *ticket = reinterpret_cast<uint32_t *>(d_desc + tiles);
+    const ShardTarget none{};
     if (cap == kNoCap)
-        compact_kernel<false><<<tiles, kCompactThreads, 0, st>>>(d_slots, slot_stride, d_sizes, packets, tile,
-                                                                 d_payload, d_desc, ticket, d_total, cap);
+        compact_kernel<false, false><<<tiles, kCompactThreads, 0, st>>>(d_slots, slot_stride, d_sizes, packets, tile,
+                                                                        d_payload, d_desc, ticket, d_total, cap, none);
     else
-        compact_kernel<true><<<tiles, kCompactThreads, 0, st>>>(d_slots, slot_stride, d_sizes, packets, tile,
-                                                                d_payload, d_desc, ticket, d_total, cap);
+        compact_kernel<true, false><<<tiles, kCompactThreads, 0, st>>>(d_slots, slot_stride, d_sizes, packets, tile,
+                                                                       d_payload, d_desc, ticket, d_total, cap, none);
     count_launch();
     return cudaGetLastError();
 }
 
-cudaError_t launch_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, uint32_t rank, uint32_t world,
-                                uint8_t *const *segments, uint32_t n_segments, uint64_t seg_cap, uint64_t *d_layout,
-                                cudaStream_t st)
+// d_desc: compact_desc_bytes(packets) + 16 bytes (the two accumulator words of the totals kernel
+// sit behind the descriptors and the ticket)
+cudaError_t launch_compact_sharded(const uint8_t *d_slots, uint32_t slot_stride, const uint32_t *d_sizes,
+                                   uint32_t packets, uint64_t *d_desc, uint64_t *d_layout, const ShardPlace &where,
+                                   uint64_t call, cudaStream_t st)
 {
-    if (n_segments == 0 || n_segments > 16 || world > 16) return cudaErrorInvalidValue;
-    SegmentList list{};
-    for (uint32_t g = 0; g < n_segments; ++g) list.base[g] = segments[g];
+    if (where.world < 1 || where.world > kMaxRanks || where.rank >= where.world || where.n_segments < 1 ||
+        where.n_segments > kMaxRanks)
+        return cudaErrorInvalidValue;
+    ShardTarget tg{};
+    for (uint32_t g = 0; g < where.n_segments; ++g) tg.segment[g] = where.segment[g];
+    for (uint32_t r = 0; r < where.world; ++r) tg.mailbox[r] = where.mailbox[r];
+    tg.seg_cap = where.seg_cap;
+    tg.rank = where.rank;
+    tg.world = where.world;
+    tg.n_segments = where.n_segments;
+    tg.tag = (uint32_t)(call % 0xFFFFFull) + 1u;
+    tg.parity = (uint32_t)(call & 1u);
+    const uint32_t tile = compact_tile_for(packets);
+    const uint32_t tiles = packets ? (packets + tile - 1) / tile : 1u;   // a rank without packets still takes part
+    cudaError_t e = cudaMemsetAsync(d_desc, 0, ((size_t)tiles + 4) * sizeof(uint64_t), st);
+    if (e != cudaSuccess) return e;
+    uint32_t *ticket = reinterpret_cast<uint32_t *>(d_desc + tiles);
+    uint64_t *acc = d_desc + tiles + 1;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    shard_concat_kernel<<<(unsigned)sms * 4u, kConcatThreads, 0, st>>>(d_payload, d_totals, rank, world, list,
-                                                                        n_segments, seg_cap, d_layout);
-    count_launch();
+    const uint32_t grid = (uint32_t)min((size_t)sms, ((size_t)packets + 2047) / 2048 + 1);
+    shard_total_kernel<<<grid, 256, 0, st>>>(d_sizes, packets, acc, tg);
+    compact_kernel<false, true><<<tiles, kCompactThreads, 0, st>>>(d_slots, slot_stride, d_sizes, packets, tile, nullptr,
+                                                                   d_desc, ticket, d_layout, kNoCap, tg);
+    count_launch(2);
     return cudaGetLastError();
 }
 

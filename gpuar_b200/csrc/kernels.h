@@ -24,13 +24,26 @@ cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const u
                            uint32_t packets, uint8_t *d_payload, uint64_t *d_desc, uint64_t *d_total,
                            cudaStream_t st, uint64_t cap = kNoCap);
 
-cudaError_t launch_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, uint32_t rank, uint32_t world,
-                                uint8_t *const *segments, uint32_t n_segments, uint64_t seg_cap, uint64_t *d_layout,
-                                cudaStream_t st);
+// Multi-GPU: the rank's packets go straight from the slots to their final place in the stream
+// concatenated over all ranks (segments, local or peer-mapped); the ranks' totals are exchanged
+// through peer-written mailboxes (encode.cu).  `call` = per-context counter of sharded encode
+// calls, equal on every rank.  d_layout = u64[5]: bytes of all ranks, segment size, this rank's
+// base offset, this rank's bytes, status.
+struct ShardPlace {
+    uint8_t *segment[16];
+    uint64_t *mailbox[16];
+    uint64_t seg_cap;
+    uint32_t rank, world, n_segments;
+};
+cudaError_t launch_compact_sharded(const uint8_t *d_slots, uint32_t slot_stride, const uint32_t *d_sizes,
+                                   uint32_t packets, uint64_t *d_desc, uint64_t *d_layout, const ShardPlace &where,
+                                   uint64_t call, cudaStream_t st);
 
-// decode.cu: d_offsets == nullptr means packet p starts at p * stride (reference slot layout)
+// decode.cu: d_offsets == nullptr means packet p starts at p * stride (reference slot layout);
+// d_count != nullptr: the packet count is read on the device (min(*d_count, packets); `packets` sizes the grid)
 cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint64_t *d_offsets, uint32_t stride,
-                          uint32_t packets, uint8_t *d_out, uint32_t packet, cudaStream_t st);
+                          uint32_t packets, uint8_t *d_out, uint32_t packet, cudaStream_t st,
+                          const uint64_t *d_count = nullptr);
 
 // index.cu
 // sizes[p] = min(rawLen of the packet at d_offsets[p], packet): what decode writes for packet p
@@ -39,5 +52,13 @@ cudaError_t launch_raw_sizes(const uint8_t *d_payload, size_t c, const uint64_t 
 size_t index_scratch_bytes(size_t c);
 cudaError_t launch_index(const uint8_t *d_payload, size_t c, uint64_t *d_offsets, size_t max_packets,
                          uint64_t *d_result, void *d_scratch, size_t scratch_bytes, uint32_t packet, cudaStream_t st);
+
+// Sharded decode: packet chain of this rank's segment of a stream of stream_bytes bytes laid out in
+// `world` segments of seg_bytes (index.cu).  Offsets are local to the segment; d_result as
+// index_finish_kernel documents.  Segments must be readable kShardHalo bytes past seg_cap.
+constexpr uint32_t kShardHalo = 8704 + 512;           // GPUAR_SHARD_HALO: a packet plus the decoder's over-read
+cudaError_t launch_index_segment(const ShardPlace &where, uint64_t call, uint64_t stream_bytes, uint64_t seg_bytes,
+                                 uint64_t *d_offsets, size_t max_packets, uint64_t *d_result, void *d_scratch,
+                                 size_t scratch_bytes, cudaStream_t st);
 
 }  // namespace gpuar

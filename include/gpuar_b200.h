@@ -166,18 +166,71 @@ int gpuar_b200_check_header(const uint8_t hdr[20]);
  * cudaIpcOpenMemHandle mapping.  Asynchronous on `stream`. */
 int gpuar_b200_peer_concat(uint8_t *d_dst, int dst_device, size_t dst_offset, const uint8_t *d_src,
                            int src_device, size_t bytes, void *stream);
-/* The same without a host round trip (what bench.py --gpus N uses): one kernel per rank reads
- * the W payload totals from device memory (d_totals[world], e.g. all-gathered), takes its
- * exclusive scan at `rank` as the landing offset and stores d_payload[0..totals[rank]) into the
- * concatenated stream with 16-byte stores over NVLink.  The stream is laid out in n_segments
- * equal segments of S = ceil(total / n_segments) bytes (rounded up to 256): global offset o is
- * byte o % S of segments[o / S]; segments[] are host-array device pointers, local or peer-mapped
- * (IPC), each with capacity seg_cap.  n_segments = world with segment g on GPU g keeps every
- * GPU's ingress at S bytes; n_segments = 1 gathers the whole stream into one buffer (then S =
- * seg_cap).  d_layout (optional, device u64[3]) receives total, S and this rank's base offset. */
-int gpuar_b200_shard_concat(const uint8_t *d_payload, const uint64_t *d_totals, int rank, int world,
-                            uint8_t *const *segments, int n_segments, size_t seg_cap, uint64_t *d_layout,
-                            void *stream);
+/* ---------------------------------------------------- sharded encode (one input, W GPUs)
+ * Packets are independent (gpuar_kernel.cu:901-907), so rank r of W encodes a contiguous packet
+ * range of the input and the .gip payload is the concatenation of the ranks' streams in rank
+ * order.  gpuar_b200_encode_sharded does that without a host round trip, without NCCL and without
+ * a second pass over the payload: after its encode kernel a rank sums its packet sizes and stores
+ * the total into every rank's MAILBOX (peer stores over NVLink); its size scan + compaction kernel
+ * waits for the W totals of this call in its own mailbox, takes their exclusive scan as its
+ * landing offset, and writes every packet straight to its final place in the concatenated stream.
+ *
+ * The stream is laid out in n_segments equal segments of S = ceil(total / n_segments) bytes
+ * (rounded up to 256): global offset o is byte o % S of segments[o / S].  n_segments = world with
+ * segment g on GPU g keeps every GPU's ingress at S bytes (with balanced shards almost nothing
+ * crosses NVLink); n_segments = 1 gathers the whole stream into one buffer.
+ *
+ * gpuar_b200_shard describes the group from ONE rank's point of view; every pointer in it is a
+ * device pointer valid on that rank's device: its own allocation, or a peer's mapped with
+ * gpuar_b200_ipc_open (one process per GPU) or made accessible with gpuar_b200_enable_peer (one
+ * process, several GPUs).  Mailboxes are GPUAR_MAILBOX_BYTES each, zeroed once before the first
+ * call.  `calls` is the library's per-context call counter: zero it once, never touch it again;
+ * all ranks must make the same sequence of sharded calls (they are collective: a rank that does
+ * not call leaves the others waiting -- for at most a few seconds, then status 2). */
+#define GPUAR_MAX_RANKS 16
+#define GPUAR_MAILBOX_BYTES 1024u
+typedef struct gpuar_b200_shard {
+    int32_t rank, world;                     /* this rank; number of ranks, <= GPUAR_MAX_RANKS          */
+    int32_t n_segments;                      /* world, or 1                                             */
+    int32_t reserved;
+    uint64_t seg_cap;                        /* capacity of every segment, bytes                        */
+    uint8_t *segments[GPUAR_MAX_RANKS];      /* [n_segments]                                            */
+    uint64_t *mailbox[GPUAR_MAX_RANKS];      /* [world]; mailbox[rank] is this rank's own               */
+    uint64_t calls[4];                       /* library state: zero once                                */
+} gpuar_b200_shard;
+
+/* d_in[n] = this rank's packet range (n a multiple of 8192 on every rank but the last).
+ *   d_layout   device u64[5]: [0] bytes of the whole concatenated stream, [1] segment size S,
+ *              [2] this rank's landing offset, [3] this rank's bytes, [4] status: 0 ok, 1 a segment
+ *              is smaller than S (nothing was written), 2 a peer's total did not arrive.
+ *   d_scratch  gpuar_b200_encode_scratch_bytes(n); the rank's own payload buffer is not needed. */
+int gpuar_b200_encode_sharded(gpuar_b200_shard *shard, const uint8_t *d_in, size_t n, uint64_t *d_layout,
+                              uint32_t *d_packet_sizes, void *d_scratch, size_t scratch_bytes, void *stream);
+
+/* ---------------------------------------------------- sharded decode (one stream, W GPUs)
+ * The stream of stream_bytes bytes lies in world segments of S = gpuar_b200_shard_segment_bytes
+ * bytes, segment g on GPU g -- the layout gpuar_b200_encode_sharded writes with n_segments = world
+ * (or a .gip payload cut into equal pieces by any other means).  Every segment must be allocated
+ * GPUAR_SHARD_HALO bytes larger than seg_cap.  The stream must be complete and visible on every
+ * GPU before the call (synchronise the ranks after the encode).
+ * Every rank discovers the packet chain of its own segment in parallel (a segment starts in the
+ * middle of a packet: where its first packet begins, and how many packets precede it, arrives
+ * from the rank before through the mailbox -- the only serial step, a few microseconds per rank)
+ * and decodes the packets that START in its segment; the tail of the last one is read from the
+ * head of the next segment, copied behind the rank's own first.  The result stays sharded: the
+ * rank's k-th packet is written at d_out + k * 8192.
+ *   d_result  device u64[8]: [0] packets decoded by this rank, [1] their raw bytes, [2] status
+ *             (0, or a GPUAR_E_* code as two's complement; GPUAR_E_ARG: out_cap too small),
+ *             [3] packets before this rank's first = index of its first packet in the stream,
+ *             [4] raw bytes before it = where d_out belongs in the decoded file.
+ *   d_scratch gpuar_b200_decode_sharded_scratch_bytes(S, out_cap / 8192). */
+#define GPUAR_SHARD_HALO (8704u + 512u)
+uint64_t gpuar_b200_shard_segment_bytes(uint64_t stream_bytes, int n_segments);
+size_t gpuar_b200_decode_sharded_scratch_bytes(uint64_t seg_bytes, size_t max_packets);
+int gpuar_b200_decode_sharded(gpuar_b200_shard *shard, uint64_t stream_bytes, uint8_t *d_out, size_t out_cap,
+                              uint64_t *d_result, void *d_scratch, size_t scratch_bytes, void *stream);
+/* one process, several GPUs: lets kernels on the current device reach memory of `peer_device` */
+int gpuar_b200_enable_peer(int peer_device);
 /* plain cudaMalloc/cudaFree on the current device: IPC-exportable allocations for the gather buffer */
 int gpuar_b200_device_alloc(size_t bytes, void **d_ptr);
 int gpuar_b200_device_free(void *d_ptr);
