@@ -195,10 +195,11 @@ def decompress(gip, out: np.ndarray | None = None, out_cap: int | None = None) -
     if out is None:
         if out_cap is None:
             # The header field is 32 bit in reference-written files.  Images written by this library
-            # carry (and mark) the high half; for an unmarked image that could hold 4 GiB or more the
-            # size comes from a hop over its packet headers (one read per packet).
+            # carry (and mark) the high half; for an unmarked image that COULD hold 4 GiB or more (8192
+            # equal bytes code into 210, so from ~110 MB of payload on) the size comes from a hop over
+            # its packet headers (one read per packet).
             out_cap = raw_size(g)
-            if g.size >= (1 << 32) - (1 << 28) and (g[3] != 0xB2 or out_cap < (1 << 32)):
+            if g.size >= FILE_HEADER and g[3] != 0xB2 and (g.size // 210 + 1) * PACKET >= (1 << 32):
                 out_cap = walk(g)[1]
         out = np.empty(out_cap + PACKET, dtype=np.uint8)
     n_out = C.c_size_t(0)

@@ -2,6 +2,7 @@
 vectors.  Bit-exact: this is integer/byte work.  Run on the B200 box: pytest -m gpu."""
 import ctypes as C
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -335,6 +336,29 @@ def test_beyond_4gib_header_and_round_trip(dev, codec):
     # prefix property: the first 1 MiB of the payload is the golden payload of mixed(31, 1 MiB)
     head = O.encode(D.mixed(31, 1 << 20))
     assert np.array_equal(payload[: head.size].cpu().numpy(), head)
+    del back, offsets
+    # SURVEY 8f-3 interop: the reference's CPU decoder (cpu_compressor.cpp:47-78 semantics: hops over the
+    # compLen fields, ignores the header) reads the whole > 4 GiB device-encoded stream
+    host_x = x.cpu().numpy()
+    host_pay = payload[:c].cpu().numpy()
+    if O.have_ref():
+        got = O.ref_decode(host_pay, n, os.cpu_count() or 1)
+        assert got.size == n and np.array_equal(got, host_x)
+        del got
+    # ... and the host-buffer path with an image of 4 GiB and more: written and read with 64-bit sizes
+    # (marked in header byte 3), and read when the header is the reference's (32-bit field wrapped,
+    # undefined bytes garbage): then the size comes from a hop over the packet headers
+    del x, payload
+    torch.cuda.empty_cache()
+    g = codec.compress(host_x)
+    assert g.size == 20 + c and g[3] == 0xB2 and codec.raw_size(g) == n
+    assert np.array_equal(g[20:], host_pay)
+    assert np.array_equal(codec.decompress(g), host_x)
+    ref_style = g.copy()
+    for k in O.HEADER_MASKED:
+        ref_style[k] = 0x5A
+    assert codec.raw_size(ref_style) == n % (1 << 32) and codec.walk(ref_style) == (packets, n)
+    assert np.array_equal(codec.decompress(ref_style), host_x)
 
 
 def test_corrupt_streams_never_fault(dev, codec):
