@@ -351,6 +351,9 @@ class Rig:
                 sys.stdout.flush()
                 os.dup2(saved, 1)
                 os.close(saved)
+        # a second group on the host (gloo): a rank that waits in an NCCL barrier spins in a kernel on its GPU, and
+        # that GPU is needed by rank 0's process during the single-process multi-GPU end-to-end leg
+        self.host_pg = dist.new_group(backend="gloo") if self.world > 1 else None
         self.dev = codec.DeviceCodec(self.local)
         _lib.set_option(_lib.OPT_ENCODE_PATH, {"auto": 0, "fused": 1, "ws": 2}[args.encode_path])
         if args.work_unit:
@@ -366,6 +369,14 @@ class Rig:
         if self.world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def host_barrier(self):
+        """All ranks meet on the HOST: the GPUs stay idle while they wait."""
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.host_pg)
 
     def timed(self, step, k):
         """K steps, each bracketed by CUDA events on the launching stream, L2 flushed in between."""
@@ -552,40 +563,62 @@ def measure(rig, workload, steps, warmup, sampler=None, with_cpu_baseline=False)
     _lib.profile(False)
     launches = _lib.launch_count() - launches0
 
-    # ---- e2e through the host-buffer entry points, pinned host memory (every rank its own shard)
+    # ---- e2e: ONE input in pinned host memory -> ONE .gip image in pinned host memory through the library's
+    # host entry point (H2D + kernels + D2H inside the timed region).  N > 1: rank 0's process drives all N GPUs
+    # with gpuar_b200_compress_host_multi (chunks rotate over the devices); the other ranks wait.
     if world > 1:
         del out
         out = None
-    host_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-    host_in.copy_(x)
-    host_gip = torch.empty(20 + codec.payload_bound(n), dtype=torch.uint8, pin_memory=True)   # e2e: 8192-byte packets
-    host_out = torch.empty(n + 8192, dtype=torch.uint8, pin_memory=True)
-    np_in, np_gip, np_out = host_in.numpy(), host_gip.numpy(), host_out.numpy()
-    e2e_steps = max(1, min(steps, 3 if n >= (1 << 30) else 5))
-    g = codec.compress(np_in, out=np_gip)
-    codec.decompress(g, out=np_out)
-    rig.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        g = codec.compress(np_in, out=np_gip)
-    torch.cuda.synchronize()
-    t_e2e_enc = (time.perf_counter() - t0) / e2e_steps
-    rig.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        back = codec.decompress(g, out=np_out)
-    torch.cuda.synchronize()
-    t_e2e_dec = (time.perf_counter() - t0) / e2e_steps
-    assert back.size == n and np.array_equal(back[:4096], np_in[:4096]) and np.array_equal(back[-4096:], np_in[-4096:])
-    gip_bytes = int(g.size)
-    del host_in, host_gip, host_out, np_in, np_gip, np_out, g, back
+    torch.cuda.empty_cache()
+    t_e2e_enc = t_e2e_dec = t_link = 0.0
+    gip_bytes = 0
+    host_n = n if world == 1 else job
+    devices = None if world == 1 else list(range(world))
+    rig.host_barrier()
+    if rank == 0:
+        host_in = torch.empty(host_n, dtype=torch.uint8, pin_memory=True)
+        if world == 1:
+            host_in.copy_(x)
+        else:
+            for a in range(0, job, 1 << 29):
+                b = min(job, a + (1 << 29))
+                host_in[a:b].copy_(x[a - b0: b - b0] if (a >= b0 and b <= b1) else gen_device(gen, seed, a, b - a))
+        host_gip = torch.empty(20 + codec.payload_bound(host_n), dtype=torch.uint8, pin_memory=True)   # e2e: 8192-byte packets
+        host_out = torch.empty(host_n + 8192, dtype=torch.uint8, pin_memory=True)
+        np_in, np_gip, np_out = host_in.numpy(), host_gip.numpy(), host_out.numpy()
+        e2e_steps = max(1, min(steps, 3 if host_n >= (1 << 30) else 5))
+        g = codec.compress(np_in, out=np_gip, devices=devices)
+        back = codec.decompress(g, out=np_out, devices=devices)
+        assert back.size == host_n and np.array_equal(back, np_in), "host path does not round-trip"
+        gip_bytes = int(g.size)
+        if world > 1:
+            # the image assembled from N devices' chunks is the reference's stream: head against the golden md5
+            gp2 = golden_prefix(gen, seed)
+            if gp2 and gip_bytes - 20 >= gp2[0]:
+                parity["e2e_image_prefix_md5"] = hashlib.md5(g[20: 20 + gp2[0]].tobytes()).hexdigest() == gp2[1]
+                assert parity["e2e_image_prefix_md5"]
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            g = codec.compress(np_in, out=np_gip, devices=devices)
+        t_e2e_enc = (time.perf_counter() - t0) / e2e_steps
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            back = codec.decompress(g, out=np_out, devices=devices)
+        t_e2e_dec = (time.perf_counter() - t0) / e2e_steps
+        # the same transfers without the kernels: the ceiling of the links + host memory for this pattern
+        codec.link_probe(np_in, np_out, gip_bytes - 20, devices=devices)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            codec.link_probe(np_in, np_out, gip_bytes - 20, devices=devices)
+        t_link = (time.perf_counter() - t0) / e2e_steps
+        del host_in, host_gip, host_out, np_in, np_gip, np_out, g, back
+    rig.host_barrier()
 
     # ---- max over ranks (per-step seconds)
-    times = torch.tensor([t_enc / steps, t_dec / steps, t_e2e_enc, t_e2e_dec, t_local / steps, t_gather / steps],
-                         dtype=torch.float64, device="cuda")
+    times = torch.tensor([t_enc / steps, t_dec / steps, t_local / steps, t_gather / steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_enc, t_dec, t_e2e_enc, t_e2e_dec, t_local, t_gather = (float(v) for v in times.tolist())
+    t_enc, t_dec, t_local, t_gather = (float(v) for v in times.tolist())
 
     res = None
     if rank == 0:
@@ -601,11 +634,16 @@ def measure(rig, workload, steps, warmup, sampler=None, with_cpu_baseline=False)
             "decode": {"value": job / t_dec / GB, "unit": "GB/s", "ms_per_step": t_dec * 1e3,
                        "includes": "device packet-chain discovery + decode kernel" +
                                    (" (every rank: its own segment of the concatenated stream)" if world > 1 else "")},
-            "e2e": {"value": job / t_e2e_enc / GB, "unit": "GB/s", "h2d_bytes_per_step": n,
-                    "d2h_bytes_per_step": gip_bytes - 20, "api": "gpuar_b200_compress_host (pinned host buffers)" +
-                    (", every rank its own shard" if world > 1 else "")},
+            "e2e": {"value": job / t_e2e_enc / GB, "unit": "GB/s", "h2d_bytes_per_step": host_n,
+                    "d2h_bytes_per_step": gip_bytes - 20,
+                    "api": "gpuar_b200_compress_host (pinned host buffers)" if world == 1 else
+                           f"gpuar_b200_compress_host_multi: one process, one host thread, {world} GPUs, one input -> one .gip image",
+                    "link_ceiling": {"value": job / t_link / GB, "unit": "GB/s",
+                                     "what": "gpuar_b200_host_link_probe: the same chunks up and the same bytes down on the "
+                                             "same streams, no kernels (PCIe links + host memory for this pattern)"}},
             "e2e_decode": {"value": job / t_e2e_dec / GB, "unit": "GB/s", "h2d_bytes_per_step": gip_bytes - 20,
-                           "d2h_bytes_per_step": n, "api": "gpuar_b200_decompress_host"},
+                           "d2h_bytes_per_step": host_n,
+                           "api": "gpuar_b200_decompress_host" if world == 1 else "gpuar_b200_decompress_host_multi"},
             "parity": parity,
             "gpu_launches": launches,
             "kernels_ms_per_step": {k: per(k) for k in spans},

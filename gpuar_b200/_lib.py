@@ -51,6 +51,9 @@ SIGNATURES = {
     "gpuar_b200_decode_ex": (C.c_int, [_vp, _sz, _sz, _vp, _sz, _vp, _sz, _vp]),
     "gpuar_b200_compress_host": (C.c_int, [_vp, _sz, _vp, _sz, C.POINTER(_sz)]),
     "gpuar_b200_decompress_host": (C.c_int, [_vp, _sz, _vp, _sz, C.POINTER(_sz)]),
+    "gpuar_b200_compress_host_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
+    "gpuar_b200_decompress_host_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, _vp, _sz, _vp, _sz, C.POINTER(_sz)]),
+    "gpuar_b200_host_link_probe": (C.c_int, [C.POINTER(C.c_int), C.c_int, _vp, _sz, _vp, _sz]),
     "gpuar_b200_gip_raw_size": (C.c_int, [_vp, _sz, C.POINTER(C.c_uint64)]),
     "gpuar_b200_gip_walk": (C.c_int, [_vp, _sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gpuar_b200_write_header": (None, [_vp, C.c_uint64, C.c_uint64]),

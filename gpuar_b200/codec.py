@@ -159,8 +159,16 @@ def _as_u8(a) -> np.ndarray:
     return np.frombuffer(bytes(a), dtype=np.uint8)
 
 
-def compress(data, out: np.ndarray | None = None) -> np.ndarray:
-    """.gip image (20-byte header + payload) of `data`, via gpuar_b200_compress_host."""
+def _device_list(devices):
+    if devices is None:
+        return None, 1
+    arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+    return arr, len(devices)
+
+
+def compress(data, out: np.ndarray | None = None, devices=None) -> np.ndarray:
+    """.gip image (20-byte header + payload) of `data`, via gpuar_b200_compress_host[_multi].
+    devices: list of CUDA device ordinals to spread the chunks over (None = the current device)."""
     init()
     src = _as_u8(data)
     cap = FILE_HEADER + payload_bound(src.size)
@@ -168,9 +176,18 @@ def compress(data, out: np.ndarray | None = None) -> np.ndarray:
         out = np.empty(cap, dtype=np.uint8)
     assert out.size >= cap
     n_out = C.c_size_t(0)
-    check(lib().gpuar_b200_compress_host(src.ctypes.data if src.size else None, src.size, out.ctypes.data, out.size,
-                                         C.byref(n_out)), "gpuar_b200_compress_host")
+    devs, nd = _device_list(devices)
+    check(lib().gpuar_b200_compress_host_multi(devs, nd, src.ctypes.data if src.size else None, src.size,
+                                               out.ctypes.data, out.size, C.byref(n_out)), "gpuar_b200_compress_host_multi")
     return out[: n_out.value]
+
+
+def link_probe(src: np.ndarray, out: np.ndarray, out_bytes: int, devices=None) -> None:
+    """The host<->device transfers of :func:`compress` without the kernels (gpuar_b200_host_link_probe)."""
+    init()
+    devs, nd = _device_list(devices)
+    check(lib().gpuar_b200_host_link_probe(devs, nd, src.ctypes.data, src.size, out.ctypes.data, min(out_bytes, out.size)),
+          "gpuar_b200_host_link_probe")
 
 
 def raw_size(gip) -> int:
@@ -188,8 +205,8 @@ def walk(gip) -> tuple[int, int]:
     return int(packets.value), int(raw.value)
 
 
-def decompress(gip, out: np.ndarray | None = None, out_cap: int | None = None) -> np.ndarray:
-    """Inverse of :func:`compress`, via gpuar_b200_decompress_host."""
+def decompress(gip, out: np.ndarray | None = None, out_cap: int | None = None, devices=None) -> np.ndarray:
+    """Inverse of :func:`compress`, via gpuar_b200_decompress_host[_multi]."""
     init()
     g = _as_u8(gip)
     if out is None:
@@ -203,8 +220,9 @@ def decompress(gip, out: np.ndarray | None = None, out_cap: int | None = None) -
                 out_cap = walk(g)[1]
         out = np.empty(out_cap + PACKET, dtype=np.uint8)
     n_out = C.c_size_t(0)
-    check(lib().gpuar_b200_decompress_host(g.ctypes.data, g.size, out.ctypes.data, out.size, C.byref(n_out)),
-          "gpuar_b200_decompress_host")
+    devs, nd = _device_list(devices)
+    check(lib().gpuar_b200_decompress_host_multi(devs, nd, g.ctypes.data, g.size, out.ctypes.data, out.size,
+                                                 C.byref(n_out)), "gpuar_b200_decompress_host_multi")
     return out[: n_out.value]
 
 

@@ -7,7 +7,6 @@
 #include <atomic>
 #include <cstring>
 #include <cstdlib>
-#include <mutex>
 #include <vector>
 
 namespace gpuar {
@@ -86,71 +85,6 @@ struct Scope {                                   // one timed span on stream st
         g_spans.push_back(s);
     }
 };
-
-// ---- per-device cache of staging buffers for the host-buffer entry points
-struct DeviceBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t need(size_t bytes)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
-    }
-};
-constexpr int kLanes = 16;                       // chunks in flight in the host-buffer pipelines
-struct HostPath {
-    int device = -1;
-    cudaStream_t stream[kLanes] = {}, copy = nullptr;
-    // All host->device copies go through `up` and all device->host copies through `down`, in chunk
-    // order: copies issued on different streams share the link in time slices, so that every chunk
-    // arrives late; in order, chunk k is complete after (k+1)/chunks of the transfer time.
-    cudaStream_t up = nullptr, down = nullptr;
-    cudaEvent_t done[kLanes] = {}, arrived[kLanes] = {}, drained[kLanes] = {}, ready = nullptr;
-    DeviceBuf in[kLanes], pay[kLanes], scratch[kLanes];
-    DeviceBuf big_in, big_out, big_scratch, offsets, result;
-    uint64_t *h_total = nullptr;                 // pinned: per-lane payload totals
-    uint64_t *h_offsets = nullptr;               // pinned: packet offsets found by the host chain walk
-    size_t h_offsets_cap = 0;
-};
-static std::mutex g_mu;
-static std::vector<HostPath *> g_paths;
-
-// tuning aid: GPUAR_B200_HOST_CHUNKS=<n> overrides the chunk count of the host-buffer pipelines
-static size_t host_chunks(size_t dflt)
-{
-    static const long v = [] { const char *e = getenv("GPUAR_B200_HOST_CHUNKS"); return e ? atol(e) : 0L; }();
-    return v > 0 ? (size_t)v : dflt;
-}
-
-static int host_path(HostPath **out)
-{
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return GPUAR_E_NODEVICE;
-    for (HostPath *h : g_paths)
-        if (h->device == dev) { *out = h; return 0; }
-    HostPath *h = new HostPath();
-    h->device = dev;
-    for (int i = 0; i < kLanes; ++i) {
-        if ((e = cudaStreamCreateWithFlags(&h->stream[i], cudaStreamNonBlocking)) != cudaSuccess) return ck(e);
-        if ((e = cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming)) != cudaSuccess) return ck(e);
-        if ((e = cudaEventCreateWithFlags(&h->arrived[i], cudaEventDisableTiming)) != cudaSuccess) return ck(e);
-        if ((e = cudaEventCreateWithFlags(&h->drained[i], cudaEventDisableTiming)) != cudaSuccess) return ck(e);
-    }
-    if ((e = cudaStreamCreateWithFlags(&h->up, cudaStreamNonBlocking)) != cudaSuccess) return ck(e);
-    if ((e = cudaStreamCreateWithFlags(&h->down, cudaStreamNonBlocking)) != cudaSuccess) return ck(e);
-    if ((e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking)) != cudaSuccess) return ck(e);
-    if ((e = cudaEventCreateWithFlags(&h->ready, cudaEventDisableTiming)) != cudaSuccess) return ck(e);
-    if ((e = cudaMallocHost(&h->h_total, (kLanes + 8) * sizeof(uint64_t))) != cudaSuccess) return ck(e);
-    g_paths.push_back(h);
-    *out = h;
-    return 0;
-}
 
 }  // namespace gpuar
 
@@ -420,224 +354,6 @@ int gpuar_b200_gip_walk(const uint8_t *gip, size_t gip_bytes, uint64_t *packets,
     }
     if (packets) *packets = n;
     if (raw_bytes) *raw_bytes = raw;
-    return 0;
-}
-
-/* ------------------------------------------------ host-buffer entry points */
-int gpuar_b200_compress_host(const uint8_t *in, size_t n, uint8_t *gip, size_t gip_cap, size_t *gip_bytes)
-{
-    if (!gip || !gip_bytes || (n && !in)) return GPUAR_E_ARG;
-    if (gip_cap < GPUAR_FILE_HEADER + gpuar_b200_payload_bound(n)) return GPUAR_E_ARG;
-    std::lock_guard<std::mutex> lock(g_mu);
-    HostPath *h = nullptr;
-    int rc = host_path(&h);
-    if (rc) return rc;
-
-    // Chunks rotate over kLanes sets of device buffers: the input of chunk k travels on the `up`
-    // stream, its kernels run on lane k % kLanes, its payload leaves on the `down` stream; the host
-    // only waits for the 8-byte total of a chunk (written by the compaction kernel straight into
-    // pinned memory) to know where the next one lands in the image.  A chunk's kernels take about
-    // the same time from 1 to ~10 000 packets (a packet is a serial chain of 8192 steps), so the
-    // end-to-end time is roughly H2D(everything) + one kernel latency + D2H(last chunk): small
-    // inputs are cut into kLanes chunks to shorten that tail (2..32 measured at 64 MiB with
-    // tools/e2e_timeline.cu and tools/e2e_sweep.py: flat from 8 to 16, worse outside), large ones
-    // into 64 MiB chunks to keep enough packets in flight.
-    size_t chunk = align_up(n / host_chunks(kLanes) + 1, kPacket);
-    chunk = chunk < ((size_t)2 << 20) ? ((size_t)2 << 20) : chunk > ((size_t)64 << 20) ? ((size_t)64 << 20) : chunk;
-    const size_t chunks = (n + chunk - 1) / chunk;
-    size_t pos = GPUAR_FILE_HEADER;
-    cudaError_t e = cudaSuccess;
-    auto drain = [&](size_t k) -> cudaError_t {
-        const int l = (int)(k % kLanes);
-        cudaError_t er = cudaEventSynchronize(h->done[l]);
-        if (er != cudaSuccess) return er;
-        const size_t bytes = (size_t)h->h_total[l];
-        er = cudaMemcpyAsync(gip + pos, h->pay[l].p, bytes, cudaMemcpyDeviceToHost, h->down);
-        if (er == cudaSuccess) er = cudaEventRecord(h->drained[l], h->down);
-        pos += bytes;
-        return er;
-    };
-    for (size_t k = 0; k < chunks && e == cudaSuccess; ++k) {
-        const int l = (int)(k % kLanes);
-        const size_t off = k * chunk, m = (n - off < chunk) ? n - off : chunk;
-        const EncodePlan p = encode_plan(m);
-        cudaStream_t st = h->stream[l];
-        if (k >= (size_t)kLanes) {
-            // lane l is reused: its input buffer is free (the host has seen done[l]), its payload
-            // and scratch once the copy of the previous occupant has left
-            e = drain(k - kLanes);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->drained[l], 0);
-        }
-        if (e == cudaSuccess) e = h->in[l].need(align_up(m, 16) + 16);
-        if (e == cudaSuccess) e = h->pay[l].need(gpuar_b200_payload_bound(m) + 16);
-        if (e == cudaSuccess) e = h->scratch[l].need(p.total);
-        if (e != cudaSuccess) break;
-        e = cudaMemcpyAsync(h->in[l].p, in + off, m, cudaMemcpyHostToDevice, h->up);
-        if (e == cudaSuccess) e = cudaEventRecord(h->arrived[l], h->up);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->arrived[l], 0);
-        if (e != cudaSuccess) break;
-        rc = gpuar_b200_encode((const uint8_t *)h->in[l].p, m, (uint8_t *)h->pay[l].p, h->pay[l].cap,
-                               &h->h_total[l], nullptr, h->scratch[l].p, h->scratch[l].cap, st);
-        if (rc) break;
-        e = cudaEventRecord(h->done[l], st);
-    }
-    for (size_t k = (chunks > (size_t)kLanes ? chunks - kLanes : 0); k < chunks && e == cudaSuccess && rc == 0; ++k)
-        e = drain(k);
-    if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(h->down);
-    if (e != cudaSuccess || rc) {
-        // errors in mid-stream: nothing may still be reading or writing the caller's buffers on return
-        for (int l = 0; l < kLanes; ++l) cudaStreamSynchronize(h->stream[l]);
-        cudaStreamSynchronize(h->up);
-        cudaStreamSynchronize(h->down);
-        return rc ? rc : ck(e);
-    }
-    gpuar_b200_write_header(gip, n, pos);
-    *gip_bytes = pos;
-    return 0;
-}
-
-int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *out, size_t out_cap,
-                               size_t *out_bytes)
-{
-    if (!gip || !out_bytes) return GPUAR_E_ARG;
-    uint64_t raw = 0;
-    int rc = gpuar_b200_gip_raw_size(gip, gip_bytes, &raw);
-    if (rc) return rc;
-    const size_t c = gip_bytes - GPUAR_FILE_HEADER;
-    if (c == 0) { *out_bytes = 0; return 0; }
-    std::lock_guard<std::mutex> lock(g_mu);
-    HostPath *h = nullptr;
-    if ((rc = host_path(&h))) return rc;
-    const uint8_t *pay = gip + GPUAR_FILE_HEADER;
-
-    // The payload is in host memory, so the packet chain is walked here, one u16 per packet, as
-    // the reference's host driver does while it reads the file (gpu_compressor.cpp:294-320) -- but
-    // only to cut the stream into chunks of whole packets that flow through kLanes streams:
-    // H2D(chunk k+1) | decode(chunk k) | D2H(chunk k-1).  (Device-resident callers use
-    // gpuar_b200_index, the parallel chain discovery on the device.)  A decode launch takes about
-    // the same time from 1 packet to a full wave, so the end-to-end time is roughly
-    // H2D(everything) + one decode latency + D2H(last chunk).
-    cudaError_t e = h->big_in.need(align_up(c, 16) + GPUAR_PAD_BYTES + 16);
-    if (e != cudaSuccess) return ck(e);
-    uint8_t *d_pay = (uint8_t *)h->big_in.p;
-    size_t chunk_bytes = c / host_chunks(kLanes) + 1;                    // payload bytes per chunk, before rounding to packets
-    if (chunk_bytes < ((size_t)2 << 20)) chunk_bytes = (size_t)2 << 20;
-    if (chunk_bytes > ((size_t)256 << 20)) chunk_bytes = (size_t)256 << 20;
-
-    // Offsets for as many packets as a stream of full packets has; a stream with short packets in
-    // it (never written by the reference) may hold more: grown on demand, below.
-    size_t max_packets = out_cap / kPacket + 2;
-    auto drain_all = [&]() -> cudaError_t {
-        cudaError_t first = cudaSuccess;
-        for (int l = 0; l < kLanes; ++l) {
-            const cudaError_t es = cudaStreamSynchronize(h->stream[l]);
-            if (first == cudaSuccess) first = es;
-        }
-        cudaError_t es = cudaStreamSynchronize(h->up);
-        if (first == cudaSuccess) first = es;
-        es = cudaStreamSynchronize(h->down);
-        return first == cudaSuccess ? es : first;
-    };
-    auto reserve_offsets = [&](size_t want, size_t keep) -> cudaError_t {
-        if (h->h_offsets_cap < want) {
-            uint64_t *fresh = nullptr;
-            cudaError_t er = cudaMallocHost(&fresh, want * sizeof(uint64_t));
-            if (er != cudaSuccess) return er;
-            if (keep) memcpy(fresh, h->h_offsets, keep * sizeof(uint64_t));
-            if (h->h_offsets) cudaFreeHost(h->h_offsets);
-            h->h_offsets = fresh;
-            h->h_offsets_cap = want;
-        }
-        return h->offsets.need(want * sizeof(uint64_t));
-    };
-    if ((e = reserve_offsets(max_packets, 0)) != cudaSuccess) return ck(e);
-    // a chunk of full packets holds at most chunk_bytes / 210 of them (8192 equal bytes code into
-    // 210); the bound only cuts chunks of short packets, whose scratch is sized by the packet count
-    const size_t chunk_packets = chunk_bytes / 128 + 1024;
-    // device mirror of the output: chunk k lands at its raw offset rounded up to 16 bytes.  Chunks end
-    // after chunk_bytes of payload or chunk_packets packets (a packet is at least 5 bytes), so there
-    // are at most this many of them; every launch is checked against the capacity again below.
-    const size_t chunks_bound = c / chunk_bytes + (c / 5) / chunk_packets + 3;
-    if ((e = h->big_out.need(out_cap + 16 * chunks_bound + kPacket + 64)) != cudaSuccess) return ck(e);
-    if ((e = cudaMemsetAsync(d_pay + c, 0, GPUAR_PAD_BYTES, h->stream[0])) != cudaSuccess) return ck(e);
-    if ((e = cudaEventRecord(h->ready, h->stream[0])) != cudaSuccess) return ck(e);
-
-    // errors in mid-stream: nothing may still be reading the caller's buffers (or ours) on return
-    auto fail = [&](int code) { drain_all(); return code; };
-    size_t pos = 0, packets = 0, total = 0, lane = 0, dev_pos = 0;
-    int status = 0;
-    while (pos < c && status == 0) {
-        // one chunk: whole packets until chunk_bytes of payload
-        const size_t p0 = packets, a = pos, raw0 = total;
-        const size_t dev0 = dev_pos;
-        bool ragged = false;                                             // a short packet that is not the chunk's last
-        size_t last_raw = kPacket;
-        while (pos < c && pos - a < chunk_bytes && packets - p0 < chunk_packets) {
-            if (c - pos < kHdr) { status = GPUAR_E_FORMAT; break; }
-            const size_t len = (size_t)pay[pos] | ((size_t)pay[pos + 1] << 8);
-            const size_t r = (size_t)pay[pos + 2] | ((size_t)pay[pos + 3] << 8);
-            if (len <= kHdr || len > c - pos) { status = GPUAR_E_FORMAT; break; }
-            if (r == 0 || r > kPacket) { status = GPUAR_E_UNSUPPORTED; break; }
-            if (total + r > out_cap || !out) { status = GPUAR_E_ARG; break; }
-            if (packets >= max_packets) {
-                // more packets than full ones would make: wait for the chunks in flight (they read
-                // the offset arrays), then double the arrays
-                e = drain_all();
-                if (e == cudaSuccess) e = reserve_offsets(max_packets * 2, packets);
-                if (e != cudaSuccess) return fail(ck(e));
-                max_packets *= 2;
-            }
-            ragged = ragged || last_raw != kPacket;
-            last_raw = r;
-            h->h_offsets[packets++] = pos;
-            total += r;
-            pos += len;
-        }
-        if (status) break;
-        const size_t m = packets - p0;
-        if (!m) break;
-        const int l = (int)(lane % kLanes);
-        cudaStream_t st = h->stream[l];
-        ++lane;
-        if (lane == 1) e = cudaSuccess; else e = cudaStreamWaitEvent(st, h->ready, 0);   // padding is in place
-        // H2D of this chunk's bytes (rounded out to 16) and of its offsets on the `up` stream (in
-        // chunk order), decode on the lane's stream, D2H on the `down` stream
-        const size_t a16 = a & ~(size_t)15, b16 = align_up(pos, 16) < c ? align_up(pos, 16) : c;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_pay + a16, pay + a16, b16 - a16, cudaMemcpyHostToDevice, h->up);
-        uint64_t *d_off = (uint64_t *)h->offsets.p + p0;
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(d_off, h->h_offsets + p0, m * sizeof(uint64_t), cudaMemcpyHostToDevice, h->up);
-        if (e == cudaSuccess) e = cudaEventRecord(h->arrived[l], h->up);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->arrived[l], 0);
-        if (e != cudaSuccess) return fail(ck(e));
-        uint8_t *d_out = (uint8_t *)h->big_out.p + dev0;
-        dev_pos = align_up(dev0 + (total - raw0), 16);
-        // the strided decode writes whole 8192-byte rows for every packet but the chunk's last
-        if (dev0 + (ragged ? total - raw0 : (m - 1) * (size_t)kPacket + last_raw) > h->big_out.cap) return fail(GPUAR_E_ARG);
-        if (!ragged) {
-            rc = gpuar_b200_decode(d_pay, c, d_off, m, d_out, m * (size_t)kPacket, st);
-        } else {
-            // short packets inside the chunk (never written by the reference, legal for its CPU
-            // decoder): decode at the 8192-byte stride into the lane's scratch, then close the gaps
-            e = h->scratch[l].need(gpuar_b200_decode_packed_scratch_bytes(m, kPacket));
-            if (e != cudaSuccess) return fail(ck(e));
-            rc = gpuar_b200_decode_packed(d_pay, c, kPacket, d_off, m, d_out, total - raw0, &h->h_total[l],
-                                          h->scratch[l].p, h->scratch[l].cap, st);
-        }
-        if (rc) return fail(rc);
-        e = cudaEventRecord(h->done[l], st);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->down, h->done[l], 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out + raw0, d_out, total - raw0, cudaMemcpyDeviceToHost, h->down);
-        if (e != cudaSuccess) return fail(ck(e));
-    }
-    {
-        const cudaError_t es = drain_all();
-        if (e == cudaSuccess) e = es;
-    }
-    if (status) return status;
-    if (e != cudaSuccess) return ck(e);
-    if ((uint32_t)raw != (uint32_t)total) return GPUAR_E_FORMAT;    // header field, file_header.hpp:61-66
-    *out_bytes = total;
     return 0;
 }
 

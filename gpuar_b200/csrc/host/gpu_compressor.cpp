@@ -53,6 +53,16 @@ void GpuCompressor::chooseDevice(int id)
     device_ = id;
 }
 
+void GpuCompressor::useDevices(const std::vector<int> &ids)
+{
+    if (ids.empty()) throw std::runtime_error("useDevices: empty device list");
+    const int count = gpuar_b200_device_count();
+    for (int id : ids)
+        if (id < 0 || id >= count) throw std::runtime_error("no such CUDA device: " + std::to_string(id));
+    chooseDevice(ids[0]);
+    devices_ = ids;
+}
+
 void GpuCompressor::reserve(std::size_t inBytes, std::size_t outBytes, bool secondInput)
 {
     // Page-locking is the expensive part of start-up (the kernel faults in and pins every page,
@@ -126,7 +136,8 @@ CompressionInfo GpuCompressor::compress(ProgressMonitor *monitor)
         proc.start();
         std::size_t image = 0;
         // write(i-1) may still be running on out_[b^1]; out_[b] is free (write(i-2) finished before write(i-1) started)
-        check(gpuar_b200_compress_host(in_[b], got, out_[b], outCap_, &image), "gpuar_b200_compress_host");
+        check(gpuar_b200_compress_host_multi(devices_.empty() ? nullptr : devices_.data(), (int)std::max<std::size_t>(devices_.size(), 1),
+                                             in_[b], got, out_[b], outCap_, &image), "gpuar_b200_compress_host");
         proc.stop();
         io.start();
         if (writing.valid() && !writing.get()) throw std::runtime_error("Write compressed data to output file failed");
@@ -222,7 +233,8 @@ CompressionInfo GpuCompressor::decompress(ProgressMonitor *monitor)
         std::uint8_t *image = pay + begin - kFileHeader;         // a .gip image of just this segment
         gpuar_b200_write_header(image, raw, kFileHeader + (cut - begin));
         std::size_t got = 0;
-        check(gpuar_b200_decompress_host(image, kFileHeader + (cut - begin), out_[ob], outCap_, &got),
+        check(gpuar_b200_decompress_host_multi(devices_.empty() ? nullptr : devices_.data(), (int)std::max<std::size_t>(devices_.size(), 1),
+                                               image, kFileHeader + (cut - begin), out_[ob], outCap_, &got),
               "gpuar_b200_decompress_host");
         proc.stop();
         if (got != raw) throw std::runtime_error("Incorrect file format");

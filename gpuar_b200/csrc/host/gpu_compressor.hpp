@@ -1,6 +1,8 @@
 // gpu_compressor.hpp -- file <-> device driver over the C ABI (mirrors gip::GPUCompressor,
 // reference src/gpu_compressor.hpp:8-39).
 #pragma once
+#include <vector>
+
 #include "compressor.hpp"
 
 namespace gip {
@@ -13,6 +15,7 @@ class GpuCompressor : public Compressor {
     std::size_t inCap_ = 0, inCap1_ = 0, outCap_ = 0;
     std::size_t segmentBytes_;         // raw bytes handled per library call (multiple of 8192)
     int device_ = -1;                  // chooseDevice() argument; -1 = the process default (device 0)
+    std::vector<int> devices_;         // useDevices(): the segments' chunks rotate over these GPUs (empty = device_ alone)
 
     void reserve(std::size_t inBytes, std::size_t outBytes, bool secondInput);
 
@@ -20,6 +23,7 @@ class GpuCompressor : public Compressor {
     explicit GpuCompressor(std::size_t segmentBytes = (std::size_t)128 << 20);
     ~GpuCompressor() override;
     void chooseDevice(int id);                                  // gpu_compressor.cpp:67-82, but really selects it
+    void useDevices(const std::vector<int> &ids);               // --gpus=N: several GPUs of the box for one file
     CompressionInfo compress(ProgressMonitor *monitor) override;
     CompressionInfo decompress(ProgressMonitor *monitor) override;
 };

@@ -11,6 +11,7 @@
 #include <iostream>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "../../../include/gpuar_b200.h"
 #include "cpu_compressor.hpp"
@@ -31,6 +32,7 @@ void usage()
                  "--help          print this help message\n"
                  "--host          run the codec on the host CPU (single thread), otherwise on the CUDA device\n"
                  "--device=N      CUDA device to use (default 0)\n"
+                 "--gpus=N        spread the file over N GPUs of the box, starting at --device (default 1)\n"
                  "--segment=MiB   raw bytes handed to the device per call (default 128)\n"
                  "--nointeractive accepted for compatibility\n";
 }
@@ -79,7 +81,11 @@ int main(int argc, char **argv)
         option(argc, argv, "out", outName);
         int device = 0;
         if (option(argc, argv, "device", value)) device = std::atoi(value.c_str());
-        std::size_t segment = (std::size_t)128 << 20;
+        int gpus = 1;
+        if (option(argc, argv, "gpus", value)) gpus = std::atoi(value.c_str());
+        if (gpus < 1 || gpus > GPUAR_MAX_RANKS) throw std::runtime_error("--gpus must be between 1 and 16");
+        // one GPU codes 128 MiB per library call; several GPUs get proportionally more per call
+        std::size_t segment = ((std::size_t)128 << 20) * (std::size_t)gpus;
         if (option(argc, argv, "segment", value)) segment = (std::size_t)std::atoll(value.c_str()) << 20;
 
         std::unique_ptr<Compressor> compressor;
@@ -91,8 +97,10 @@ int main(int argc, char **argv)
             // process uses one.  Unless the caller set a mask already, show the driver only that
             // device (it then is device 0 of the process): on an 8-GPU box start-up is ~8x shorter.
             if (!std::getenv("CUDA_VISIBLE_DEVICES") && device >= 0) {
-                setenv("CUDA_VISIBLE_DEVICES", std::to_string(device).c_str(), 1);
-                if (device > 0) std::cout << "Choose CUDA device: " << device << "." << std::endl;
+                std::string mask;
+                for (int g = 0; g < gpus; ++g) mask += (g ? "," : "") + std::to_string(device + g);
+                setenv("CUDA_VISIBLE_DEVICES", mask.c_str(), 1);
+                if (device > 0 || gpus > 1) std::cout << "Choose CUDA device: " << mask << "." << std::endl;
                 device = 0;
             }
             const auto t0 = std::chrono::steady_clock::now();
@@ -101,7 +109,11 @@ int main(int argc, char **argv)
             trace("driver start-up (device count)", t0);
             auto *gpu = new GpuCompressor(segment);
             compressor.reset(gpu);
-            if (device > 0) {
+            if (gpus > 1) {
+                std::vector<int> ids;
+                for (int g = 0; g < gpus; ++g) ids.push_back(device + g);
+                gpu->useDevices(ids);
+            } else if (device > 0) {
                 std::cout << "Choose CUDA device: " << device << "." << std::endl;
                 gpu->chooseDevice(device);
             }

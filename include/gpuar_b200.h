@@ -143,6 +143,23 @@ int gpuar_b200_decode_ex(const uint8_t *d_payload, size_t c, size_t packet_bytes
 int gpuar_b200_compress_host(const uint8_t *in, size_t n, uint8_t *gip, size_t gip_cap, size_t *gip_bytes);
 int gpuar_b200_decompress_host(const uint8_t *gip, size_t gip_bytes, uint8_t *out, size_t out_cap,
                                size_t *out_bytes);
+/* The same over several GPUs of the box, from ONE host thread of one process: the chunks rotate
+ * over the devices (chunk k on devices[k mod n_devices]), every device's PCIe link carries its own
+ * chunks up and down, and the image is assembled in place (a chunk's payload is copied to its final
+ * position as soon as the totals of the chunks before it are known).  devices = NULL means the
+ * current device alone (exactly the plain entry points).  Host buffers should be page-locked
+ * (gpuar_b200_host_alloc) for the copies to run at link speed.  Calls that share a device are
+ * serialised per device; calls on disjoint devices run concurrently. */
+int gpuar_b200_compress_host_multi(const int *devices, int n_devices, const uint8_t *in, size_t n, uint8_t *gip,
+                                   size_t gip_cap, size_t *gip_bytes);
+int gpuar_b200_decompress_host_multi(const int *devices, int n_devices, const uint8_t *gip, size_t gip_bytes,
+                                     uint8_t *out, size_t out_cap, size_t *out_bytes);
+/* Measurement hook: the transfers of gpuar_b200_compress_host_multi without its kernels -- the same
+ * chunks of in[n] go up on the same streams and out_bytes come down, spread over the chunks.
+ * Synchronous; the caller times it.  What the PCIe links and the host memory behind them can do
+ * for this access pattern: the ceiling of the end-to-end numbers. */
+int gpuar_b200_host_link_probe(const int *devices, int n_devices, const uint8_t *in, size_t n, uint8_t *out,
+                               size_t out_bytes);
 /* raw size announced by a .gip image (walks nothing: header field, 32-bit in the
  * reference's layout, 64-bit when written by this library -- see DESIGN.md). */
 int gpuar_b200_gip_raw_size(const uint8_t *gip, size_t gip_bytes, uint64_t *raw_bytes);
