@@ -59,7 +59,7 @@ class PeerGroup:
         per_rank = int(want.item())
         # a segment holds ceil(total / n_segments) <= the largest per-rank bound (+ rounding), plus
         # the head of the next segment for the decode side
-        cap = (per_rank + 4096 + HALO if self.layout == "segments" else per_rank * self.world + HALO) + 256
+        cap = (max(per_rank + 4096, 16384) + HALO if self.layout == "segments" else per_rank * self.world + HALO) + 256
         cap = (cap + 255) & ~255
         if self.shard is not None and cap <= self.cap:
             return

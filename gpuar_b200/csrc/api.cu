@@ -415,7 +415,7 @@ uint64_t gpuar_b200_shard_segment_bytes(uint64_t stream_bytes, int n_segments)
 {
     if (n_segments < 1) return 0;
     const uint64_t seg = ((stream_bytes + (uint64_t)n_segments - 1) / (uint64_t)n_segments + 255) & ~(uint64_t)255;
-    return seg ? seg : 256;                          /* what the compaction kernel computes (shard_segment_bytes) */
+    return seg < GPUAR_SHARD_MIN_SEGMENT ? GPUAR_SHARD_MIN_SEGMENT : seg;   /* what the compaction kernel computes (shard_segment_bytes) */
 }
 
 /* sharded decode scratch: [offsets: max_packets * 8][index scratch of one segment] */

@@ -421,29 +421,75 @@ GPUAR_HD uint32_t tree_level(uint64_t &node, uint32_t &rem, uint32_t &room)
     return c;
 }
 
+// The same level for the THROUGHPUT decoder (many warps per scheduler): there the integer ALU pipe
+// is the roof (it issues one warp instruction every two cycles, as does the FMA pipe, and this
+// path has 89 ALU-pipe against 58 FMA-pipe instructions per step), so everything that can be
+// phrased as a multiply-add moves to the FMA pipe.  The three comparison bits are the child index
+// AND the update: "+1 on every slot above c" is slot1 += 1 - b0, slot2 += 1 - b1, slot3 += 1 - b2
+// (b_j = rem >= t_j; slots never carry into each other), i.e. multiply-adds on the two halves
+// instead of a 64-bit variable shift and a carry chain; and "room stays if c == 3" is
+// x + b2 * (room - x) instead of a compare and a predicated subtract.
+#ifndef GPUAR_DEC_FMA
+#define GPUAR_DEC_FMA 3             // tuning knob: bit 0 = node update, bit 1 = room select as multiply-adds
+#endif
+GPUAR_HD uint32_t mad32(uint32_t a, uint32_t b, uint32_t c)       // a * b + c on the FMA pipe
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    return a * b + c;
+#endif
+}
+GPUAR_HD uint32_t tree_level_fma(uint64_t &node, uint32_t &rem, uint32_t &room)
+{
+    const uint32_t lo = (uint32_t)node, hi = (uint32_t)(node >> 32);
+    const uint32_t rr = rem * 0x10001u + 0x80008000u;
+    const uint32_t dlo = rr - lo, dhi = rr - hi;
+    const uint32_t b0 = dlo >> 31, b1 = (dhi >> 15) & 1u, b2 = dhi >> 31;
+    const uint32_t c = b0 + b1 + b2;
+    const uint32_t p = prmt(dlo, dhi, 0x3210u + 0x2222u * c);     // slot c | slot c+1 << 16
+    rem = p & 0x7FFFu;
+    const uint32_t x = 0x8000u - (p >> 16);
+    if (GPUAR_DEC_FMA & 2) room = mad32(b2, room - x, x);         // c == 3 <=> b2
+    else room = c == 3u ? room : x;
+    if (GPUAR_DEC_FMA & 1) {
+        const uint32_t nlo = mad32(b0, 0xFFFF0000u, lo + 0x10000u);               // slot1 += 1 - b0
+        const uint32_t nhi = mad32(b2, 0xFFFF0000u, hi + 0x10001u) - b1;          // slot2 += 1 - b1, slot3 += 1 - b2
+        node = ((uint64_t)nhi << 32) | nlo;
+    } else {
+        node += 0x0001000100010000ull << (16u * c);
+    }
+    return c;
+}
+
 // Finds the symbol whose cumulative interval holds `target` (getSymbolFromProbability,
 // :727-763), returns it with lo = cum[s], cnt = count[s], and bumps count[s] (:288).
 GPUAR_HD uint32_t tree_decode(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t target, uint32_t total,
                               uint32_t &lo, uint32_t &cnt)
 {
+    auto level = [](uint64_t &node, uint32_t &rem, uint32_t &room) {
+        return GPUAR_DEC_FMA ? tree_level_fma(node, rem, room) : tree_level(node, rem, room);
+    };
     uint32_t rem = target, room = total - target;
-    uint32_t idx = tree_level(root, rem, room);
+    uint32_t idx = level(root, rem, room);
     {
         uint64_t *n = nodes + idx * stride;
         uint64_t v = *n;
-        idx = idx * 4u + tree_level(v, rem, room);
+        idx = idx * 4u + level(v, rem, room);
         *n = v;
     }
     {
         uint64_t *n = nodes + (4u + idx) * stride;
         uint64_t v = *n;
-        idx = idx * 4u + tree_level(v, rem, room);
+        idx = idx * 4u + level(v, rem, room);
         *n = v;
     }
     {
         uint64_t *n = nodes + (20u + idx) * stride;
         uint64_t v = *n;
-        idx = idx * 4u + tree_level(v, rem, room);
+        idx = idx * 4u + level(v, rem, room);
         *n = v;
     }
     lo = target - rem;
@@ -476,6 +522,7 @@ GPUAR_HD uint32_t pick4(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t a, uint3
 // with two bitwise selects on the sign masks of the threshold tests -- a shared-memory round
 // trip (~30 cycles) on the dependent chain becomes ~10 cycles of logic, for three more loads
 // and six selects per level.  Same result as tree_decode_early_range.
+template <int kSpec>
 GPUAR_HD uint32_t tree_decode_spec_range(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t code,
                                          uint32_t L, uint32_t range, uint32_t T, uint32_t &lo, uint32_t &cnt)
 {
@@ -501,7 +548,7 @@ GPUAR_HD uint32_t tree_decode_spec_range(uint64_t &root, uint64_t *nodes, uint32
     // level-2 candidates of that child
     uint64_t *const g2 = nodes + (4u + c0 * 4u) * stride;
     uint64_t a2 = 0, b2 = 0, c2n = 0, d2n = 0;
-    if (GPUAR_DEC_SPEC & 2) {
+    if (kSpec & 2) {
         a2 = g2[0];
         b2 = g2[stride];
         c2n = g2[2u * stride];
@@ -516,14 +563,14 @@ GPUAR_HD uint32_t tree_decode_spec_range(uint64_t &root, uint64_t *nodes, uint32
     uint64_t *const p2 = g2 + c1 * stride;
     uint64_t *const g3 = nodes + (20u + idx * 4u) * stride;
     uint64_t a3 = 0, b3 = 0, c3n = 0, d3n = 0;
-    if (GPUAR_DEC_SPEC & 4) {
+    if (kSpec & 4) {
         a3 = g3[0];
         b3 = g3[stride];
         c3n = g3[2u * stride];
         d3n = g3[3u * stride];
     }
     uint64_t n2;
-    if (GPUAR_DEC_SPEC & 2) {
+    if (kSpec & 2) {
         const uint32_t lo2 = pick4(k0, k1, k2, (uint32_t)a2, (uint32_t)b2, (uint32_t)c2n, (uint32_t)d2n);
         const uint32_t hi2 = pick4(k0, k1, k2, (uint32_t)(a2 >> 32), (uint32_t)(b2 >> 32), (uint32_t)(c2n >> 32),
                                    (uint32_t)(d2n >> 32));
@@ -537,7 +584,7 @@ GPUAR_HD uint32_t tree_decode_spec_range(uint64_t &root, uint64_t *nodes, uint32
     // levels 2 and 3 on the quotient
     const uint32_t target = divide_exact(num, range);
     uint32_t rem = target - below1, room = above1 - target;
-    if (GPUAR_DEC_SPEC & 4) {
+    if (kSpec & 4) {
         // the four leaf nodes below (c0, c1) were requested before the quotient existed
         const uint32_t z0 = (uint32_t)n2, z1 = (uint32_t)(n2 >> 32);
         const uint32_t rr = rem * 0x10001u + 0x80008000u;
@@ -566,10 +613,11 @@ GPUAR_HD uint32_t tree_decode_spec_range(uint64_t &root, uint64_t *nodes, uint32
     return idx;
 }
 
+template <int kSpec = GPUAR_DEC_SPEC>
 GPUAR_HD uint32_t tree_decode_early_range(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t code,
                                           uint32_t L, uint32_t range, uint32_t T, uint32_t &lo, uint32_t &cnt)
 {
-    if (GPUAR_DEC_SPEC) return tree_decode_spec_range(root, nodes, stride, code, L, range, T, lo, cnt);
+    if (kSpec) return tree_decode_spec_range<kSpec>(root, nodes, stride, code, L, range, T, lo, cnt);
     const uint32_t num = (((code - L) & 0xFFFFu) + 1u) * T - 1u;
     // "threshold * range <= num" as the sign of num - threshold * range (everything < 2^30): one
     // multiply-add and one shift per threshold, no predicates (their write-to-use latency is

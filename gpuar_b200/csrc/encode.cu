@@ -33,6 +33,9 @@ namespace gpuar {
 // ------------------------------------------------------------------ encode
 struct EncShared {
     uint64_t tree[kTreeStored][32];  // 21504 B; lane l owns column l (banks 2l, 2l+1); root in registers
+#ifdef GPUAR_OCC_PAD
+    uint8_t pad[GPUAR_OCC_PAD];      // occupancy experiment: fewer CTAs per SM
+#endif
 };
 
 __global__ void __launch_bounds__(32)
@@ -301,7 +304,7 @@ __device__ __forceinline__ uint64_t shard_segment_bytes(const ShardTarget &tg, u
 {
     if (tg.n_segments <= 1) return tg.seg_cap;
     const uint64_t seg = ((all + tg.n_segments - 1) / tg.n_segments + 255) & ~(uint64_t)255;
-    return seg ? seg : 256;
+    return seg < kMinSegment ? kMinSegment : seg;            // a packet never spans more than two segments
 }
 
 // kGuard: the destination holds `cap` bytes and the sizes come from an untrusted stream (the
@@ -388,7 +391,12 @@ compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const ui
             const uint8_t *src = slots + (size_t)(first + q) * slot_stride;
             const uint32_t head = (uint32_t)min((uint64_t)len, seg - in);
             warp_copy_unaligned(tg.segment[g] + in, src, head, lane);
-            if (head < len) warp_copy_any(tg.segment[g + 1u], src + head, len - head, lane);   // straddles a boundary
+            uint32_t done = head;                                  // the rest straddles a boundary (or, with
+            for (uint64_t h = g + 1u; done < len; ++h) {           // gather-sized segments, never gets here)
+                const uint32_t part = (uint32_t)min((uint64_t)(len - done), seg);
+                warp_copy_any(tg.segment[h], src + done, part, lane);
+                done += part;
+            }
         }
     } else {
         for (uint32_t q = warp; q < count; q += kCompactThreads / 32u) {

@@ -14,6 +14,7 @@ namespace gpuar {
 constexpr uint32_t kMaxRanks = 16;                    // GPUAR_MAX_RANKS
 constexpr uint32_t kMailTotals = 0;                   // u64[2][16]: per-rank totals, by parity
 constexpr uint32_t kMailChain = 32;                   // u64[2][4]: chain hand-over, by parity
+constexpr uint64_t kMinSegment = 16384;               // GPUAR_SHARD_MIN_SEGMENT: more than a packet with its halo
 constexpr uint64_t kTagShift = 44;
 constexpr uint64_t kValueMask = (1ull << kTagShift) - 1ull;
 

@@ -193,7 +193,7 @@ int gpuar_b200_peer_concat(uint8_t *d_dst, int dst_device, size_t dst_offset, co
  * landing offset, and writes every packet straight to its final place in the concatenated stream.
  *
  * The stream is laid out in n_segments equal segments of S = ceil(total / n_segments) bytes
- * (rounded up to 256): global offset o is byte o % S of segments[o / S].  n_segments = world with
+ * (rounded up to 256, at least GPUAR_SHARD_MIN_SEGMENT): global offset o is byte o % S of segments[o / S].  n_segments = world with
  * segment g on GPU g keeps every GPU's ingress at S bytes (with balanced shards almost nothing
  * crosses NVLink); n_segments = 1 gathers the whole stream into one buffer.
  *
@@ -242,6 +242,7 @@ int gpuar_b200_encode_sharded(gpuar_b200_shard *shard, const uint8_t *d_in, size
  *             [4] raw bytes before it = where d_out belongs in the decoded file.
  *   d_scratch gpuar_b200_decode_sharded_scratch_bytes(S, out_cap / 8192). */
 #define GPUAR_SHARD_HALO (8704u + 512u)
+#define GPUAR_SHARD_MIN_SEGMENT 16384u   /* S never gets smaller: a packet spans at most two segments */
 uint64_t gpuar_b200_shard_segment_bytes(uint64_t stream_bytes, int n_segments);
 size_t gpuar_b200_decode_sharded_scratch_bytes(uint64_t seg_bytes, size_t max_packets);
 int gpuar_b200_decode_sharded(gpuar_b200_shard *shard, uint64_t stream_bytes, uint8_t *d_out, size_t out_cap,

@@ -96,3 +96,75 @@ def test_options_validate_their_values():
         for v in good:
             assert _lib.lib().gpuar_b200_set_option(key, v) == 0, (key, v)
     assert _lib.lib().gpuar_b200_set_option(99, 0) == _lib.E_ARG
+
+
+def test_wide_sizes_are_trusted_only_under_the_mark():
+    """Header byte 3 = GPUAR_HEADER_WIDE_MARK says bytes 8-11 / 16-19 carry the high halves of 64-bit sizes;
+    without it (reference-written files leave those bytes uninitialised, file_header.hpp:28-36,61-72) only the
+    32-bit fields count -- a stray 1 in byte 8 must not turn 20000 into 4 GiB + 20000."""
+    data = np.arange(20000, dtype=np.uint32).astype(np.uint8)
+    g = O.gip_file(data)
+    raw = C.c_uint64()
+    h = np.zeros(20, np.uint8)
+    _lib.lib().gpuar_b200_write_header(h.ctypes.data, data.size, g.size)
+    assert h[3] == 0xB2
+    g[:20] = h
+    g[8] = 1                                               # marked, but implausible for this payload: ignored
+    assert _lib.lib().gpuar_b200_gip_raw_size(g.ctypes.data, g.size, C.byref(raw)) == 0 and raw.value == 20000
+    g[3] = 0                                               # unmarked: ignored whatever it says
+    assert _lib.lib().gpuar_b200_gip_raw_size(g.ctypes.data, g.size, C.byref(raw)) == 0 and raw.value == 20000
+    # a header alone (the CLI passes 20 bytes and the file size): plausible wide size under the mark is taken
+    big_raw, big_gip = (5 << 30) + 123, (3 << 30) + 20
+    _lib.lib().gpuar_b200_write_header(h.ctypes.data, big_raw, big_gip)
+    assert _lib.lib().gpuar_b200_gip_raw_size(h.ctypes.data, big_gip, C.byref(raw)) == 0 and raw.value == big_raw
+    h[3] = 0x5A
+    assert _lib.lib().gpuar_b200_gip_raw_size(h.ctypes.data, big_gip, C.byref(raw)) == 0 and raw.value == big_raw % (1 << 32)
+
+
+def test_gip_walk_matches_the_oracle_chain():
+    """gpuar_b200_gip_walk: the host hop over compLen / rawLen (cpu_compressor.cpp:47-78), no device needed."""
+    from gpuar_b200 import datagen as D
+    packets, raw = C.c_uint64(), C.c_uint64()
+    for data in (np.zeros(0, np.uint8), D.mixed(3, 8192 * 5 + 77), D.uniform(9, 1)):
+        g = O.gip_file(data)
+        assert _lib.lib().gpuar_b200_gip_walk(g.ctypes.data, g.size, C.byref(packets), C.byref(raw)) == 0
+        assert (packets.value, raw.value) == ((data.size + 8191) // 8192, data.size)
+    # short packets in the middle: legal for the CPU decoder
+    parts = [D.uniform(1, 8192 + 5), D.and3(2, 100)]
+    pay = np.concatenate([O.encode(p) for p in parts])
+    g = np.concatenate([O.header(0, 20 + pay.size), pay])
+    assert _lib.lib().gpuar_b200_gip_walk(g.ctypes.data, g.size, C.byref(packets), C.byref(raw)) == 0
+    assert (packets.value, raw.value) == (3, 8192 + 5 + 100)
+    # broken chains
+    bad = g.copy()
+    bad[20] = 3; bad[21] = 0                               # compLen 3 <= header length
+    assert _lib.lib().gpuar_b200_gip_walk(bad.ctypes.data, bad.size, C.byref(packets), C.byref(raw)) == _lib.E_FORMAT
+    assert _lib.lib().gpuar_b200_gip_walk(g.ctypes.data, g.size - 1, C.byref(packets), C.byref(raw)) == _lib.E_FORMAT
+    bad = g.copy()
+    bad[22] = 0x01; bad[23] = 0x20                         # rawLen 8193
+    assert _lib.lib().gpuar_b200_gip_walk(bad.ctypes.data, bad.size, C.byref(packets), C.byref(raw)) == _lib.E_UNSUPPORTED
+
+
+def test_segment_layout_of_a_sharded_stream():
+    """gpuar_b200_shard_segment_bytes: equal segments, 256-byte granules, never smaller than a packet with its halo."""
+    f = _lib.lib().gpuar_b200_shard_segment_bytes
+    assert f(0, 8) == 16384 and f(5055, 8) == 16384
+    for total, n in ((10_380_379_762, 8), (67_648_274 * 8, 8), (1 << 20, 3), (1 << 40, 16)):
+        s = f(total, n)
+        assert s % 256 == 0 and s * n >= total and (s - 256) * n < total or s == 16384
+    assert f(1 << 30, 1) == 1 << 30 and f(100, 0) == 0
+    assert _lib.lib().gpuar_b200_decode_sharded_scratch_bytes(1 << 20, 200) >= 200 * 8 + _lib.lib().gpuar_b200_index_scratch_bytes(1 << 20)
+
+
+def test_sharded_entry_points_refuse_malformed_groups():
+    """argument checks of the sharded ABI come before any device work"""
+    sh = _lib.Shard()
+    lay = (C.c_uint64 * 8)()
+    for rank, world, nseg in ((0, 0, 1), (2, 2, 2), (0, 17, 17), (0, 2, 3)):
+        sh.rank, sh.world, sh.n_segments = rank, world, nseg
+        assert _lib.lib().gpuar_b200_encode_sharded(C.byref(sh), None, 0, lay, None, lay, 0, None) == _lib.E_ARG
+        assert _lib.lib().gpuar_b200_decode_sharded(C.byref(sh), 0, None, 0, lay, lay, 0, None) == _lib.E_ARG
+    devs = (C.c_int * 2)(0, 0)
+    n = C.c_size_t()
+    buf = np.zeros(20 + 8704 + 64, np.uint8)
+    assert _lib.lib().gpuar_b200_compress_host_multi(devs, 0, buf.ctypes.data, 1, buf.ctypes.data, buf.size, C.byref(n)) != 0

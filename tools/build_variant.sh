@@ -9,7 +9,7 @@ root=$(cd "$(dirname "$0")/.." && pwd)
 src=$root/gpuar_b200/csrc
 out=$src/build/variant_$name
 mkdir -p "$out"
-for f in api encode encode_ws decode index; do
+for f in api host_pipeline encode encode_ws decode index; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC "$@" \
        -c "$src/$f.cu" -o "$out/$f.o" &
 done
