@@ -47,12 +47,13 @@ static int g_encode_path = 0;                    // 0 auto, 1 fused lane=packet,
 static size_t g_ws_max_packets = (size_t)148 * 3 * 32 * 2;
 
 static cudaError_t encode_slots(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t stride, uint32_t *d_sizes,
-                                uint32_t packet, cudaStream_t st)
+                                uint32_t packet, cudaStream_t st, const ShardPlace *where = nullptr, uint64_t call = 0,
+                                uint64_t *d_acc = nullptr)
 {
     const size_t packets = packets_of(n, packet);
     const bool ws = g_encode_path == 2 || (g_encode_path == 0 && packets <= g_ws_max_packets);
-    return ws ? launch_encode_slots_ws(d_in, n, d_slots, stride, d_sizes, packet, st)
-              : launch_encode_slots(d_in, n, d_slots, stride, d_sizes, packet, st);
+    return ws ? launch_encode_slots_ws(d_in, n, d_slots, stride, d_sizes, packet, st, where, call, d_acc)
+              : launch_encode_slots(d_in, n, d_slots, stride, d_sizes, packet, st, where, call, d_acc);
 }
 
 // ---- optional per-kernel timing (bench.py's roofline): CUDA events recorded on the
@@ -399,16 +400,19 @@ int gpuar_b200_encode_sharded(gpuar_b200_shard *shard, const uint8_t *d_in, size
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t *s = static_cast<uint8_t *>(d_scratch);
     uint32_t *sizes = d_packet_sizes ? d_packet_sizes : reinterpret_cast<uint32_t *>(s + p.off_sizes);
-    cudaError_t e;
+    const ShardPlace where = shard_place(shard);
+    const uint64_t call = shard->calls[0]++;
+    uint64_t *desc = reinterpret_cast<uint64_t *>(s + p.off_desc);
+    cudaError_t e = shard_desc_reset(desc, (uint32_t)p.packets, st);
+    if (e != cudaSuccess) return ck(e);
     {
+        // the encode kernel also sums the packet sizes; its last CTA stores the total into every rank's mailbox
         Scope t(GPUAR_SPAN_ENCODE, st);
-        e = encode_slots(d_in, n, s + p.off_slots, kSlot, sizes, kPacket, st);
+        e = encode_slots(d_in, n, s + p.off_slots, kSlot, sizes, kPacket, st, &where, call, shard_acc(desc, (uint32_t)p.packets));
     }
     if (e != cudaSuccess) return ck(e);
-    const uint64_t call = shard->calls[0]++;
     Scope t(GPUAR_SPAN_COMPACT, st);
-    return ck(launch_compact_sharded(s + p.off_slots, kSlot, sizes, (uint32_t)p.packets,
-                                     reinterpret_cast<uint64_t *>(s + p.off_desc), d_layout, shard_place(shard), call, st));
+    return ck(launch_compact_sharded(s + p.off_slots, kSlot, sizes, (uint32_t)p.packets, desc, d_layout, where, call, st));
 }
 
 uint64_t gpuar_b200_shard_segment_bytes(uint64_t stream_bytes, int n_segments)

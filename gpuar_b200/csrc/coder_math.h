@@ -430,7 +430,7 @@ GPUAR_HD uint32_t tree_level(uint64_t &node, uint32_t &rem, uint32_t &room)
 // instead of a 64-bit variable shift and a carry chain; and "room stays if c == 3" is
 // x + b2 * (room - x) instead of a compare and a predicated subtract.
 #ifndef GPUAR_DEC_FMA
-#define GPUAR_DEC_FMA 3             // tuning knob: bit 0 = node update, bit 1 = room select as multiply-adds
+#define GPUAR_DEC_FMA 1             // tuning knob: bit 0 = node update, bit 1 = room select as multiply-adds (1 GiB decode, ms: 0 -> 8.18, 1 -> 8.00, 2 -> 8.35, 3 -> 8.20)
 #endif
 GPUAR_HD uint32_t mad32(uint32_t a, uint32_t b, uint32_t c)       // a * b + c on the FMA pipe
 {

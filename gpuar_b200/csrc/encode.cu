@@ -40,7 +40,7 @@ struct EncShared {
 
 __global__ void __launch_bounds__(32)
 encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ slots, uint32_t slot_stride,
-              uint32_t *__restrict__ sizes, uint32_t n_packets, uint32_t packet)
+              uint32_t *__restrict__ sizes, uint32_t n_packets, uint32_t packet, ShardTarget tg, uint64_t *__restrict__ acc)
 {
     __shared__ __align__(16) EncShared sm;
     const uint32_t lane = lane_id();
@@ -142,9 +142,14 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
     }
     if (pending) emit_symbol(out, pend, pk, pu, pU);              // BITS of the last step
 
+    uint32_t comp = 0;
     if (mine) {
-        const uint32_t comp = finish_packet(out, L, pend, slot, len);
+        comp = finish_packet(out, L, pend, slot, len);
         if (sizes) sizes[my] = comp;
+    }
+    if (tg.world > 1u) {                                          // sharded encode: this rank's total for the other ranks
+        const uint32_t sum = __reduce_add_sync(kFull, comp);
+        if (lane == 0) shard_publish_total(sum, acc, tg);
     }
 }
 
@@ -245,30 +250,6 @@ __device__ __forceinline__ void warp_copy_any(uint8_t *__restrict__ dst, const u
 //   parity = call counter & 1: a rank can be at most one call ahead of the slowest one (it needs
 //            that rank's total of call e+1, which is stream-ordered after its compaction of call
 //            e), so two buffers suffice.
-// Sum of this rank's packet sizes -> `tag | total` into every rank's mailbox.  `acc` = u64[2]
-// scratch (sum, CTAs done), zeroed by the launcher.
-__global__ void __launch_bounds__(256)
-shard_total_kernel(const uint32_t *__restrict__ sizes, uint32_t n_packets, uint64_t *__restrict__ acc, ShardTarget tg)
-{
-    uint64_t sum = 0;
-    for (size_t i = (size_t)blockIdx.x * 256u + threadIdx.x; i < n_packets; i += (size_t)gridDim.x * 256u) sum += sizes[i];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
-    __shared__ uint64_t s_part[8];
-    if (lane_id() == 0) s_part[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x) return;
-    for (int w = 1; w < 8; ++w) sum += s_part[w];
-    atomicAdd(reinterpret_cast<unsigned long long *>(&acc[0]), (unsigned long long)sum);
-    __threadfence();
-    if (atomicAdd(reinterpret_cast<unsigned long long *>(&acc[1]), 1ull) + 1ull != gridDim.x) return;
-    __threadfence();
-    const uint64_t total = ld_desc(&acc[0]);
-    const uint64_t word = ((uint64_t)tg.tag << kTagShift) | (total & kValueMask);
-    for (uint32_t r = 0; r < tg.world; ++r) st_sys(tg.mailbox[r] + kMailTotals + tg.parity * kMaxRanks + tg.rank, word);
-    __threadfence_system();
-}
-
 // Called by one full warp: the W totals of this call from the rank's own mailbox.  Returns false
 // on a timeout.  base = bytes of the ranks before this one, all = bytes of all ranks.
 __device__ __forceinline__ bool shard_totals(const ShardTarget &tg, uint32_t lane, uint64_t &base, uint64_t &all,
@@ -358,7 +339,9 @@ compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const ui
         uint64_t seg = 0;
         if (kSharded) {
             uint64_t rank_base, all, mine;
+            const uint64_t t_wait = global_ns();
             const bool ok = shard_totals(tg, lane, rank_base, all, mine);
+            if (lane == 0 && tile == 0) total_out[5] = global_ns() - t_wait;   // diagnostics: ns the first tile waited for the totals
             seg = shard_segment_bytes(tg, all);
             const uint64_t status = !ok ? 2ull : (seg > tg.seg_cap || (tg.n_segments <= 1 && all > seg)) ? 1ull : 0ull;
             if (status) seg = 0;                                    // nothing is copied
@@ -410,12 +393,37 @@ compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const ui
 // ------------------------------------------------------------------ launchers
 const void *probe_kernel() { return reinterpret_cast<const void *>(&encode_kernel); }
 
+ShardTarget shard_target(const ShardPlace &where, uint64_t call)
+{
+    ShardTarget tg{};
+    for (uint32_t g = 0; g < where.n_segments; ++g) tg.segment[g] = where.segment[g];
+    for (uint32_t r = 0; r < where.world; ++r) tg.mailbox[r] = where.mailbox[r];
+    tg.seg_cap = where.seg_cap;
+    tg.rank = where.rank;
+    tg.world = where.world;
+    tg.n_segments = where.n_segments;
+    tg.tag = (uint32_t)(call % 0xFFFFFull) + 1u;
+    tg.parity = (uint32_t)(call & 1u);
+    return tg;
+}
+
+// one thread: a rank without packets still reports its total (zero)
+__global__ void shard_publish_empty_kernel(uint64_t *acc, ShardTarget tg) { shard_publish_total(0, acc, tg); }
+
 cudaError_t launch_encode_slots(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t slot_stride,
-                                uint32_t *d_sizes, uint32_t packet, cudaStream_t st)
+                                uint32_t *d_sizes, uint32_t packet, cudaStream_t st, const ShardPlace *where,
+                                uint64_t call, uint64_t *d_acc)
 {
     const uint32_t packets = (uint32_t)((n + packet - 1) / packet);
-    if (!packets) return cudaSuccess;
-    encode_kernel<<<(packets + 31u) / 32u, 32, 0, st>>>(d_in, n, d_slots, slot_stride, d_sizes, packets, packet);
+    const ShardTarget tg = where ? shard_target(*where, call) : ShardTarget{};
+    if (!packets) {
+        if (where && where->world > 1u) {
+            shard_publish_empty_kernel<<<1, 1, 0, st>>>(d_acc, tg);
+            count_launch();
+        }
+        return cudaGetLastError();
+    }
+    encode_kernel<<<(packets + 31u) / 32u, 32, 0, st>>>(d_in, n, d_slots, slot_stride, d_sizes, packets, packet, tg, d_acc);
     count_launch();
     return cudaGetLastError();
 }
@@ -467,8 +475,21 @@ cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const u
     return cudaGetLastError();
 }
 
-// d_desc: compact_desc_bytes(packets) + 16 bytes (the two accumulator words of the totals kernel
-// sit behind the descriptors and the ticket)
+// The ranks' totals were published by the encode kernel (shard_publish_total); d_desc must have been
+// zeroed by shard_desc_reset BEFORE that kernel (its accumulator words sit behind the descriptors).
+uint64_t *shard_acc(uint64_t *d_desc, uint32_t packets)
+{
+    const uint32_t tile = compact_tile_for(packets);
+    const uint32_t tiles = packets ? (packets + tile - 1) / tile : 1u;
+    return d_desc + tiles + 1;
+}
+cudaError_t shard_desc_reset(uint64_t *d_desc, uint32_t packets, cudaStream_t st)
+{
+    const uint32_t tile = compact_tile_for(packets);
+    const uint32_t tiles = packets ? (packets + tile - 1) / tile : 1u;
+    return cudaMemsetAsync(d_desc, 0, ((size_t)tiles + 4) * sizeof(uint64_t), st);
+}
+
 cudaError_t launch_compact_sharded(const uint8_t *d_slots, uint32_t slot_stride, const uint32_t *d_sizes,
                                    uint32_t packets, uint64_t *d_desc, uint64_t *d_layout, const ShardPlace &where,
                                    uint64_t call, cudaStream_t st)
@@ -476,29 +497,13 @@ cudaError_t launch_compact_sharded(const uint8_t *d_slots, uint32_t slot_stride,
     if (where.world < 1 || where.world > kMaxRanks || where.rank >= where.world || where.n_segments < 1 ||
         where.n_segments > kMaxRanks)
         return cudaErrorInvalidValue;
-    ShardTarget tg{};
-    for (uint32_t g = 0; g < where.n_segments; ++g) tg.segment[g] = where.segment[g];
-    for (uint32_t r = 0; r < where.world; ++r) tg.mailbox[r] = where.mailbox[r];
-    tg.seg_cap = where.seg_cap;
-    tg.rank = where.rank;
-    tg.world = where.world;
-    tg.n_segments = where.n_segments;
-    tg.tag = (uint32_t)(call % 0xFFFFFull) + 1u;
-    tg.parity = (uint32_t)(call & 1u);
+    const ShardTarget tg = shard_target(where, call);
     const uint32_t tile = compact_tile_for(packets);
     const uint32_t tiles = packets ? (packets + tile - 1) / tile : 1u;   // a rank without packets still takes part
-    cudaError_t e = cudaMemsetAsync(d_desc, 0, ((size_t)tiles + 4) * sizeof(uint64_t), st);
-    if (e != cudaSuccess) return e;
     uint32_t *ticket = reinterpret_cast<uint32_t *>(d_desc + tiles);
-    uint64_t *acc = d_desc + tiles + 1;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint32_t grid = (uint32_t)min((size_t)sms, ((size_t)packets + 2047) / 2048 + 1);
-    shard_total_kernel<<<grid, 256, 0, st>>>(d_sizes, packets, acc, tg);
     compact_kernel<false, true><<<tiles, kCompactThreads, 0, st>>>(d_slots, slot_stride, d_sizes, packets, tile, nullptr,
                                                                    d_desc, ticket, d_layout, kNoCap, tg);
-    count_launch(2);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "shard.cuh"
 
 #ifndef GPUAR_WS_CODER_BLOCK
 #define GPUAR_WS_CODER_BLOCK 4      // tuning knob: steps per straight-line block of the CODER warp
@@ -153,7 +154,7 @@ __device__ __forceinline__ void model_warp(WsShared &sm, uint64_t *tree, const u
 __global__ void __launch_bounds__(kWsMaxThreads)
 encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ slots, uint32_t slot_stride,
                  uint32_t *__restrict__ sizes, uint32_t n_packets, uint32_t packet, uint32_t map_first,
-                 uint32_t map_later, uint32_t first_ctas)
+                 uint32_t map_later, uint32_t first_ctas, ShardTarget tg, uint64_t *__restrict__ acc)
 {
     extern __shared__ __align__(16) uint8_t ws_smem[];           // 72 KB: above the static limit
     WsShared &sm = *reinterpret_cast<WsShared *>(ws_smem);
@@ -315,18 +316,27 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
         }
         // final_l: written by CODER before its last "C full", which FIELD waited for before its last
         // "F full", which this warp waited for in the last round (release/acquire chain at CTA scope)
+        uint32_t comp = 0;
         if (mine) {
-            const uint32_t comp = finish_packet(out, sm.final_l[lane], pend, slot, len);
+            comp = finish_packet(out, sm.final_l[lane], pend, slot, len);
             if (sizes) sizes[my] = comp;
+        }
+        if (tg.world > 1u) {                                      // sharded encode: this rank's total for the other ranks
+            const uint32_t sum = __reduce_add_sync(kFull, comp);
+            if (lane == 0) shard_publish_total(sum, acc, tg);
         }
     }
 }
 
+ShardTarget shard_target(const ShardPlace &where, uint64_t call);     // encode.cu
+
 cudaError_t launch_encode_slots_ws(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t slot_stride,
-                                   uint32_t *d_sizes, uint32_t packet, cudaStream_t st)
+                                   uint32_t *d_sizes, uint32_t packet, cudaStream_t st, const ShardPlace *where,
+                                   uint64_t call, uint64_t *d_acc)
 {
     const uint32_t packets = (uint32_t)((n + packet - 1) / packet);
-    if (!packets) return cudaSuccess;
+    if (!packets) return launch_encode_slots(d_in, n, d_slots, slot_stride, d_sizes, packet, st, where, call, d_acc);
+    const ShardTarget tg = where ? shard_target(*where, call) : ShardTarget{};
     // per device: the attribute belongs to the function of the current context
     cudaError_t e = cudaFuncSetAttribute(encode_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(WsShared));
@@ -347,7 +357,7 @@ cudaError_t launch_encode_slots_ws(const uint8_t *d_in, size_t n, uint8_t *d_slo
     Tune t = ctas <= (uint32_t)sms ? Tune{8, kMapCoderAlone, kMapCoderAlone} : Tune{6, kMapSix, kMapSix};
     if (forced.warps) t = forced;
     encode_ws_kernel<<<ctas, 32u * t.warps, sizeof(WsShared), st>>>(d_in, n, d_slots, slot_stride, d_sizes, packets,
-                                                                     packet, t.first, t.later, (uint32_t)sms);
+                                                                     packet, t.first, t.later, (uint32_t)sms, tg, d_acc);
     count_launch();
     return cudaGetLastError();
 }

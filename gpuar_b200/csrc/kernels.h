@@ -8,13 +8,25 @@ namespace gpuar {
 
 // encode.cu
 const void *probe_kernel();   // address of a kernel of this library, for image-loadability checks
+// Multi-GPU: where a rank's stream lands (encode.cu) -- the segments of the concatenated stream and
+// the mailboxes through which the ranks exchange their totals, all local or peer-mapped.
+struct ShardPlace {
+    uint8_t *segment[16];
+    uint64_t *mailbox[16];
+    uint64_t seg_cap;
+    uint32_t rank, world, n_segments;
+};
 // `packet` = raw bytes per packet: 8192 in the reference format (gpu.h:13); any multiple of 16 up to
-// 16112 is coded correctly (the reference's own limit, compressor.cpp:13)
+// 16112 is coded correctly (the reference's own limit, compressor.cpp:13).
+// where != nullptr (sharded encode): the kernel also adds up the rank's packet sizes and its last
+// CTA stores the total into every rank's mailbox; d_acc = shard_acc(...), zeroed by shard_desc_reset.
 cudaError_t launch_encode_slots(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t slot_stride,
-                                uint32_t *d_sizes, uint32_t packet, cudaStream_t st);
+                                uint32_t *d_sizes, uint32_t packet, cudaStream_t st, const ShardPlace *where = nullptr,
+                                uint64_t call = 0, uint64_t *d_acc = nullptr);
 // encode_ws.cu: same contract, six specialised warps per 32 packets (for inputs that cannot fill the GPU)
 cudaError_t launch_encode_slots_ws(const uint8_t *d_in, size_t n, uint8_t *d_slots, uint32_t slot_stride,
-                                   uint32_t *d_sizes, uint32_t packet, cudaStream_t st);
+                                   uint32_t *d_sizes, uint32_t packet, cudaStream_t st, const ShardPlace *where = nullptr,
+                                   uint64_t call = 0, uint64_t *d_acc = nullptr);
 size_t compact_desc_bytes(size_t packets);
 bool set_compact_tile(uint32_t packets_per_tile);   // 0 = automatic, else a power of two 4..128
 // `cap` != kNoCap: d_payload holds cap bytes and the sizes are untrusted (decode side): packets that
@@ -25,16 +37,12 @@ cudaError_t launch_compact(const uint8_t *d_slots, uint32_t slot_stride, const u
                            cudaStream_t st, uint64_t cap = kNoCap);
 
 // Multi-GPU: the rank's packets go straight from the slots to their final place in the stream
-// concatenated over all ranks (segments, local or peer-mapped); the ranks' totals are exchanged
-// through peer-written mailboxes (encode.cu).  `call` = per-context counter of sharded encode
-// calls, equal on every rank.  d_layout = u64[5]: bytes of all ranks, segment size, this rank's
-// base offset, this rank's bytes, status.
-struct ShardPlace {
-    uint8_t *segment[16];
-    uint64_t *mailbox[16];
-    uint64_t seg_cap;
-    uint32_t rank, world, n_segments;
-};
+// concatenated over all ranks (segments, local or peer-mapped); the ranks' totals arrive through the
+// mailboxes (published by the encode kernel).  `call` = per-context counter of sharded encode calls,
+// equal on every rank.  d_layout = u64[5]: bytes of all ranks, segment size, this rank's base offset,
+// this rank's bytes, status.  Order on the stream: shard_desc_reset, encode (with shard_acc), compact.
+uint64_t *shard_acc(uint64_t *d_desc, uint32_t packets);
+cudaError_t shard_desc_reset(uint64_t *d_desc, uint32_t packets, cudaStream_t st);
 cudaError_t launch_compact_sharded(const uint8_t *d_slots, uint32_t slot_stride, const uint32_t *d_sizes,
                                    uint32_t packets, uint64_t *d_desc, uint64_t *d_layout, const ShardPlace &where,
                                    uint64_t call, cudaStream_t st);

@@ -63,4 +63,21 @@ __device__ __forceinline__ void mail_post(uint64_t *p, uint32_t tag, uint64_t va
     st_sys(p, ((uint64_t)tag << kTagShift) | (value & kValueMask));
 }
 
+
+// A kernel's CTAs add up this rank's payload bytes and the last one to finish stores the total into
+// every rank's mailbox.  Called by one thread per CTA with the CTA's sum; `acc` = u64[2] (sum, CTAs
+// done), zeroed before the launch.
+__device__ __forceinline__ void shard_publish_total(uint64_t cta_sum, uint64_t *acc, const ShardTarget &tg)
+{
+    atomicAdd(reinterpret_cast<unsigned long long *>(&acc[0]), (unsigned long long)cta_sum);
+    __threadfence();
+    if (atomicAdd(reinterpret_cast<unsigned long long *>(&acc[1]), 1ull) + 1ull != gridDim.x) return;
+    __threadfence();
+    uint64_t total;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(total) : "l"(&acc[0]) : "memory");
+    const uint64_t word = ((uint64_t)tg.tag << kTagShift) | (total & kValueMask);
+    for (uint32_t r = 0; r < tg.world; ++r) st_sys(tg.mailbox[r] + kMailTotals + tg.parity * kMaxRanks + tg.rank, word);
+    __threadfence_system();
+}
+
 }  // namespace gpuar

@@ -217,9 +217,10 @@ typedef struct gpuar_b200_shard {
 } gpuar_b200_shard;
 
 /* d_in[n] = this rank's packet range (n a multiple of 8192 on every rank but the last).
- *   d_layout   device u64[5]: [0] bytes of the whole concatenated stream, [1] segment size S,
+ *   d_layout   device u64[8]: [0] bytes of the whole concatenated stream, [1] segment size S,
  *              [2] this rank's landing offset, [3] this rank's bytes, [4] status: 0 ok, 1 a segment
- *              is smaller than S (nothing was written), 2 a peer's total did not arrive.
+ *              is smaller than S (nothing was written), 2 a peer's total did not arrive;
+ *              [5] diagnostics: nanoseconds the first compaction tile waited for the ranks' totals.
  *   d_scratch  gpuar_b200_encode_scratch_bytes(n); the rank's own payload buffer is not needed. */
 int gpuar_b200_encode_sharded(gpuar_b200_shard *shard, const uint8_t *d_in, size_t n, uint64_t *d_layout,
                               uint32_t *d_packet_sizes, void *d_scratch, size_t scratch_bytes, void *stream);
