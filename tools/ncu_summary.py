@@ -10,6 +10,9 @@ WANT = [
     "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
+    "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.avg.per_cycle_active",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
