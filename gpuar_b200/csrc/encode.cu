@@ -160,7 +160,12 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
 constexpr uint32_t kMaxTilePackets = 128;
 constexpr uint32_t kCompactThreads = 256;
 
-// copy `len` bytes from src (16-byte aligned) to dst (any alignment) with one warp
+// Copy `len` bytes from src to dst (any alignment each) with one warp: 16-byte stores on the destination's
+// alignment, the source read as aligned 16-byte words and shifted into place.  The source is read from
+// the 16-byte boundary at or below src up to 32 bytes past src + len: inside the slots buffer (slots are
+// 16-byte aligned and 8704 apart, a packet is at most 8281 bytes) -- also for the second piece of a
+// packet that is split at a segment boundary, whose source starts anywhere inside the slot (a byte-wise
+// copy of such a piece by a single warp took 70 us and held up the whole kernel, profiles/r2_shard_probe_trace_n8.txt).
 __device__ __forceinline__ void warp_copy_unaligned(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
                                                     uint32_t len, uint32_t lane)
 {
@@ -206,27 +211,6 @@ __device__ __forceinline__ void warp_copy_unaligned(uint8_t *__restrict__ dst, c
     }
     const uint32_t done = head + (body << 4);
     if (lane < len - done) dst[done + lane] = src[done + lane];
-}
-
-// same, but the source may have any alignment too (pieces split at segment boundaries)
-__device__ __forceinline__ void warp_copy_any(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
-                                              uint32_t len, uint32_t lane)
-{
-    if ((((uintptr_t)src) & 15u) == 0) {
-        warp_copy_unaligned(dst, src, len, lane);
-    } else if (((((uintptr_t)src) ^ ((uintptr_t)dst)) & 3u) == 0) {
-        // same phase modulo 4: byte head, 4-byte body, byte tail
-        const uint32_t head = min(len, (uint32_t)((4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u));
-        if (lane < head) dst[lane] = src[lane];
-        const uint32_t body = (len - head) >> 2;
-        const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src + head);
-        uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
-        for (uint32_t c = lane; c < body; c += 32u) d4[c] = s4[c];
-        const uint32_t done = head + (body << 2);
-        if (lane < len - done) dst[done + lane] = src[done + lane];
-    } else {
-        for (uint32_t c = lane; c < len; c += 32u) dst[c] = src[c];
-    }
 }
 
 // ------------------------------------------------- multi-GPU: where a rank's stream lands
@@ -294,6 +278,13 @@ __device__ __forceinline__ uint64_t shard_segment_bytes(const ShardTarget &tg, u
 // kSharded: the destination is the concatenated stream of all ranks (ShardTarget); `total_out`
 // = u64[5]: bytes of all ranks, segment size, this rank's base offset, this rank's bytes, status
 // (0 ok, 1 a segment is too small, 2 a peer's total never arrived).
+#ifdef GPUAR_SHARD_TRACE
+__device__ uint64_t g_shard_trace[8192 * 4];      // per tile: start, after look-back, after the totals, end (globaltimer)
+#define TRACE(slot) do { if (kSharded && threadIdx.x == 0 && tile < 8192u) g_shard_trace[tile * 4u + (slot)] = global_ns(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+
 template <bool kGuard, bool kSharded>
 __global__ void __launch_bounds__(kCompactThreads)
 compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const uint32_t *__restrict__ sizes,
@@ -310,6 +301,7 @@ compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const ui
     const uint32_t tile = s_tile;
     const uint32_t first = tile * tile_packets;
     const uint32_t count = first < n_packets ? min(tile_packets, n_packets - first) : 0u;
+    TRACE(0);
 
     if (warp == 0) {
         // exclusive scan of this tile's sizes (four per lane)
@@ -336,6 +328,7 @@ compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const ui
 
         // decoupled look-back for the bytes that precede this tile
         uint64_t base = lookback_exclusive(desc, tile, total, lane);
+        TRACE(1);
         uint64_t seg = 0;
         if (kSharded) {
             uint64_t rank_base, all, mine;
@@ -360,6 +353,7 @@ compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const ui
             s_base = base;
             s_seg = seg;
         }
+        TRACE(2);
     }
     __syncthreads();
 
@@ -377,10 +371,14 @@ compact_kernel(const uint8_t *__restrict__ slots, uint32_t slot_stride, const ui
             uint32_t done = head;                                  // the rest straddles a boundary (or, with
             for (uint64_t h = g + 1u; done < len; ++h) {           // gather-sized segments, never gets here)
                 const uint32_t part = (uint32_t)min((uint64_t)(len - done), seg);
-                warp_copy_any(tg.segment[h], src + done, part, lane);
+                warp_copy_unaligned(tg.segment[h], src + done, part, lane);
                 done += part;
             }
         }
+#ifdef GPUAR_SHARD_TRACE
+        __syncthreads();
+        TRACE(3);
+#endif
     } else {
         for (uint32_t q = warp; q < count; q += kCompactThreads / 32u) {
             if (kGuard && base + s_off[q + 1u] > cap) continue;
@@ -506,5 +504,12 @@ cudaError_t launch_compact_sharded(const uint8_t *d_slots, uint32_t slot_stride,
     count_launch();
     return cudaGetLastError();
 }
+
+#ifdef GPUAR_SHARD_TRACE
+extern "C" int gpuar_b200_debug_shard_trace(uint64_t *host, size_t words)   // tools/shard_probe.py, tracing builds only
+{
+    return (int)cudaMemcpyFromSymbol(host, g_shard_trace, words * sizeof(uint64_t));
+}
+#endif
 
 }  // namespace gpuar

@@ -65,6 +65,27 @@ def main():
             torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     w = sorted(int(t[5].item()) / 1e3 for t in waits[-2 * args.steps:])
     out["totals_wait_us"] = {"min": w[0], "med": w[len(w) // 2], "max": w[-1]}
+    # tracing build (tools/build_variant.sh trace -DGPUAR_SHARD_TRACE): per-tile time line of the last compaction
+    try:
+        import ctypes as C
+        import numpy as np
+        fn = _lib.lib().gpuar_b200_debug_shard_trace
+        tiles = (n // 8192 + 7) // 8
+        tr = np.zeros(tiles * 4, dtype=np.uint64)
+        torch.cuda.synchronize()
+        assert fn(tr.ctypes.data_as(C.c_void_p), C.c_size_t(tr.size)) == 0
+        tr = tr.reshape(tiles, 4).astype(np.int64)
+        t0 = int(tr[:, 0].min())
+        q = [0, tiles // 4, tiles // 2, 3 * tiles // 4, tiles - 1]
+        out["trace_us"] = {"tiles": tiles, "first_start": 0.0, "last_start": round((int(tr[:, 0].max()) - t0) / 1e3, 1),
+                           "last_end": round((int(tr[:, 3].max()) - t0) / 1e3, 1),
+                           "lookback_done_max": round((int(tr[:, 1].max()) - t0) / 1e3, 1),
+                           "totals_done_max": round((int(tr[:, 2].max()) - t0) / 1e3, 1),
+                           "sample_tiles[start,lookback,totals,end]": {int(t): [round((int(v) - t0) / 1e3, 1) for v in tr[t]] for t in q},
+                           "copy_us_mean": round(float((tr[:, 3] - tr[:, 2]).mean()) / 1e3, 1),
+                           "copy_us_max": round(float((tr[:, 3] - tr[:, 2]).max()) / 1e3, 1)}
+    except AttributeError:
+        pass
     rows = [None] * world
     dist.all_gather_object(rows, out)
     if rank == 0:
