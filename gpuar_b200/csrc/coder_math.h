@@ -50,37 +50,6 @@ GPUAR_HD uint32_t bswap32(uint32_t x)
 #endif
 }
 
-// ---- additions on the FMA pipe.  The integer ALU pipe and the FMA pipe each issue one warp
-// instruction every two cycles per scheduler (B300_MICROARCH: rt_SMSP = 2), and the throughput
-// encoder has 106 ALU-pipe against 44 FMA-pipe instructions per symbol step: it runs at the ALU
-// pipe's roof while the FMA pipe idles.  ptxas picks IADD3 / VIADD or IMAD.IADD by its own
-// balancing heuristic; a multiply-add whose multiplier it cannot see (a __constant__ word that the
-// host could overwrite) must stay an IMAD.  So "a + b" written as a * ONE + b is an addition that
-// is guaranteed to issue on the FMA pipe -- used where GPUAR_FMA_ADDS selects it, plain adds on
-// the host and elsewhere.
-#ifndef GPUAR_FMA_ADDS
-#define GPUAR_FMA_ADDS 0            // per translation unit: bit 0 node updates, 1 interval arithmetic, 2 bit sink, 3 model sums
-#endif
-#if defined(__CUDACC__)
-static __constant__ uint32_t k_opaque_one = 1u, k_opaque_neg = 0xFFFFFFFFu;
-#endif
-template <int kBit>
-GPUAR_HD uint32_t fadd(uint32_t a, uint32_t b)                   // a + b
-{
-#if defined(__CUDA_ARCH__)
-    if ((GPUAR_FMA_ADDS >> kBit) & 1) return a * k_opaque_one + b;
-#endif
-    return a + b;
-}
-template <int kBit>
-GPUAR_HD uint32_t fsub(uint32_t a, uint32_t b)                   // a - b
-{
-#if defined(__CUDA_ARCH__)
-    if ((GPUAR_FMA_ADDS >> kBit) & 1) return b * k_opaque_neg + a;
-#endif
-    return a - b;
-}
-
 // Division by the running total T = 256 + i (gpuar_kernel.cu:273,280) is a division by
 // a warp-uniform constant: floor(n / T) = mulhi(n, m) >> sh for every n < 2^30, with
 //   sh = floor(log2 T) - 1,   m = ceil(2^(32+sh) / T) <= 2^31.
@@ -106,22 +75,22 @@ GPUAR_HD uint32_t div_total(uint32_t n, uint32_t m, uint32_t sh) { return mulhi3
 // L = (L1 << (k+u)) & 0x7FFF, V = (V1 << (k+u)) & 0x7FFF.
 GPUAR_HD void shifts_of(uint32_t L1, uint32_t U1, uint32_t &k, uint32_t &u)
 {
-    k = fadd<1>(clz32((L1 ^ U1) & 0xFFFFu), 0u - 16u);
+    k = clz32((L1 ^ U1) & 0xFFFFu) - 16u;
     const uint32_t g = (L1 & ~U1) << k;              // positions with L=1, U=0 after the k shifts
-    u = fadd<1>(clz32(~g & 0x7FFFu), 0u - 17u);      // run of them starting at bit 14
+    u = clz32(~g & 0x7FFFu) - 17u;                   // run of them starting at bit 14
 }
 
 GPUAR_HD void narrow_renorm(uint32_t &L, uint32_t &V, uint32_t lo, uint32_t hi, uint32_t m, uint32_t sh,
                             uint32_t &k, uint32_t &u, uint32_t &U1)
 {
-    const uint32_t range = fsub<1>(fsub<1>(65536u, V), L);
+    const uint32_t range = 65536u - V - L;
     const uint32_t qa = div_total(hi * range, m, sh);
     const uint32_t qb = div_total(lo * range, m, sh);
-    const uint32_t V1 = fsub<1>(fsub<1>(65536u, L), qa);   // 0xFFFF - (L + qa - 1)
-    const uint32_t L1 = fadd<1>(L, qb);
+    const uint32_t V1 = 65536u - L - qa;             // 0xFFFF - (L + qa - 1)
+    const uint32_t L1 = L + qb;
     U1 = V1 ^ 0xFFFFu;
     shifts_of(L1, U1, k, u);
-    const uint32_t t = fadd<1>(k, u);
+    const uint32_t t = k + u;
     L = (L1 << t) & 0x7FFFu;
     V = (V1 << t) & 0x7FFFu;
 }
@@ -236,10 +205,10 @@ struct BitSink {
     GPUAR_HD void put(uint32_t val, uint32_t len)    // len <= 32, val < 2^len
     {
         acc = (acc << len) | val;
-        nb = fadd<2>(nb, len);
+        nb += len;
         const uint32_t w = (uint32_t)(acc >> (nb & 31u));          // the oldest 32 bits when nb >= 32
         if (nb >= 32u && widx < wcap) words[widx] = bswap32(w);
-        widx = fadd<2>(widx, nb >> 5);
+        widx += nb >> 5;
         nb &= 31u;
     }
 };
@@ -267,13 +236,13 @@ GPUAR_HD bool emit_is_long(uint32_t pend, uint32_t k) { return k != 0u && pend >
 GPUAR_HD void emit_field(BitSink &out, uint32_t &pend, uint32_t k, uint32_t u, uint32_t U1)
 {
     const uint32_t b = U1 >> 15;
-    const uint32_t km1 = k ? fadd<2>(k, 0u - 1u) : 0u;
-    const uint32_t rest = (U1 >> fsub<2>(16u, k)) & fadd<2>(1u << km1, 0u - 1u);
-    const uint32_t head = fsub<2>(1u << (pend & 31u), b ^ 1u);    // b, then pend x !b
+    const uint32_t km1 = k ? k - 1u : 0u;
+    const uint32_t rest = (U1 >> (16u - k)) & ((1u << km1) - 1u);
+    const uint32_t head = (1u << (pend & 31u)) - (b ^ 1u);        // b, then pend x !b
     const uint32_t val = k ? ((head << km1) | rest) : 0u;
-    const uint32_t len = k ? fadd<2>(k, pend) : 0u;
+    const uint32_t len = k ? k + pend : 0u;
     out.put(val, len);
-    pend = k ? u : fadd<2>(pend, u);
+    pend = k ? u : pend + u;
 }
 
 GPUAR_HD void emit_long(BitSink &out, uint32_t &pend, uint32_t k, uint32_t u, uint32_t U1)   // k != 0, pend > 16
@@ -452,18 +421,12 @@ GPUAR_HD uint32_t tree_level(uint64_t &node, uint32_t &rem, uint32_t &room)
     return c;
 }
 
-// The same level for the THROUGHPUT decoder (many warps per scheduler): there the integer ALU pipe
-// is the roof (it issues one warp instruction every two cycles, as does the FMA pipe, and this
-// path has 89 ALU-pipe against 58 FMA-pipe instructions per step), so everything that can be
-// phrased as a multiply-add moves to the FMA pipe.  The three comparison bits are the child index
-// AND the update: "+1 on every slot above c" is slot1 += 1 - b0, slot2 += 1 - b1, slot3 += 1 - b2
-// (b_j = rem >= t_j; slots never carry into each other), i.e. multiply-adds on the two halves
-// instead of a 64-bit variable shift and a carry chain; and "room stays if c == 3" is
-// x + b2 * (room - x) instead of a compare and a predicated subtract.
-#ifndef GPUAR_DEC_FMA
-#define GPUAR_DEC_FMA 1             // tuning knob: bit 0 = node update, bit 1 = room select as multiply-adds (1 GiB decode, ms: 0 -> 8.18, 1 -> 8.00, 2 -> 8.35, 3 -> 8.20)
-#endif
-GPUAR_HD uint32_t mad32(uint32_t a, uint32_t b, uint32_t c)       // a * b + c on the FMA pipe
+// The same level for the THROUGHPUT decoder (many warps per scheduler).  The three comparison bits are the
+// child index AND the update: "+1 on every slot above c" is slot1 += 1 - b0, slot2 += 1 - b1, slot3 += 1 - b2
+// (b_j = rem >= t_j; slots never carry into each other), i.e. two multiply-adds on the halves instead of a
+// 64-bit variable shift and a carry chain: 1 GiB decode 8.18 -> 8.00 ms.  (The `room` select as a
+// multiply-add too: 8.35 ms; measured, not kept -- profiles/r2_kernel_experiments.md.)
+GPUAR_HD uint32_t mad32(uint32_t a, uint32_t b, uint32_t c)       // a * b + c, kept a multiply-add (FMA pipe)
 {
 #if defined(__CUDA_ARCH__)
     uint32_t r;
@@ -482,16 +445,10 @@ GPUAR_HD uint32_t tree_level_fma(uint64_t &node, uint32_t &rem, uint32_t &room)
     const uint32_t c = b0 + b1 + b2;
     const uint32_t p = prmt(dlo, dhi, 0x3210u + 0x2222u * c);     // slot c | slot c+1 << 16
     rem = p & 0x7FFFu;
-    const uint32_t x = 0x8000u - (p >> 16);
-    if (GPUAR_DEC_FMA & 2) room = mad32(b2, room - x, x);         // c == 3 <=> b2
-    else room = c == 3u ? room : x;
-    if (GPUAR_DEC_FMA & 1) {
-        const uint32_t nlo = mad32(b0, 0xFFFF0000u, lo + 0x10000u);               // slot1 += 1 - b0
-        const uint32_t nhi = mad32(b2, 0xFFFF0000u, hi + 0x10001u) - b1;          // slot2 += 1 - b1, slot3 += 1 - b2
-        node = ((uint64_t)nhi << 32) | nlo;
-    } else {
-        node += 0x0001000100010000ull << (16u * c);
-    }
+    room = c == 3u ? room : 0x8000u - (p >> 16);
+    const uint32_t nlo = mad32(b0, 0xFFFF0000u, lo + 0x10000u);               // slot1 += 1 - b0
+    const uint32_t nhi = mad32(b2, 0xFFFF0000u, hi + 0x10001u) - b1;          // slot2 += 1 - b1, slot3 += 1 - b2
+    node = ((uint64_t)nhi << 32) | nlo;
     return c;
 }
 
@@ -500,9 +457,7 @@ GPUAR_HD uint32_t tree_level_fma(uint64_t &node, uint32_t &rem, uint32_t &room)
 GPUAR_HD uint32_t tree_decode(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t target, uint32_t total,
                               uint32_t &lo, uint32_t &cnt)
 {
-    auto level = [](uint64_t &node, uint32_t &rem, uint32_t &room) {
-        return GPUAR_DEC_FMA ? tree_level_fma(node, rem, room) : tree_level(node, rem, room);
-    };
+    auto level = [](uint64_t &node, uint32_t &rem, uint32_t &room) { return tree_level_fma(node, rem, room); };
     uint32_t rem = target, room = total - target;
     uint32_t idx = level(root, rem, room);
     {
@@ -547,28 +502,6 @@ GPUAR_HD uint32_t pick4(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t a, uint3
     return bsel(m1, bsel(m0, a, b), bsel(m2, c, d));
 }
 
-// The same select as multiply-adds: d + m2 (d - c) + m1 (c - b) + m0 (b - a) with the masks as -1 / 0.  Three
-// instructions deep instead of two, but on the FMA pipe: the latency-oriented decoder issues 150 ALU-pipe against
-// 65 FMA-pipe instructions per step from a single warp, and each pipe takes one instruction every two cycles, so
-// its step cannot be shorter than 300 cycles however short the dependent chain is.  The differences do not depend
-// on the masks (off the chain).  GPUAR_DEC_PICK selects which selects are built this way.
-#ifndef GPUAR_DEC_PICK
-#define GPUAR_DEC_PICK 0            // tuning knob: bit 0 below/above sums, 1 level-1 node + remainder, 2 level-2 node, 3 leaf node
-#endif
-template <int kBit>
-GPUAR_HD uint32_t pick4x(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{
-#if defined(__CUDA_ARCH__)
-    if ((GPUAR_DEC_PICK >> kBit) & 1) {
-        const uint32_t dc = d * k_opaque_one - c * k_opaque_one;   // kept as multiply-adds: FMA pipe
-        const uint32_t cb = c * k_opaque_one - b * k_opaque_one;
-        const uint32_t ba = b * k_opaque_one - a * k_opaque_one;
-        return (m2 * dc + d) + (m1 * cb + m0 * ba);
-    }
-#endif
-    return pick4(m0, m1, m2, a, b, c, d);
-}
-
 // Variant of tree_decode_early_range whose node loads do not wait for the child index: the
 // four candidates of the next level are loaded as soon as their parent is known (level 1: at
 // the top of the step, level 2: once the level-0 child is known) and the right one is picked
@@ -591,12 +524,12 @@ GPUAR_HD uint32_t tree_decode_spec_range(uint64_t &root, uint64_t *nodes, uint32
     const uint32_t m0 = mask(e0), m1 = mask(e1), m2 = mask(e2);
     const uint32_t c0 = 3u + m0 + m1 + m2;
     uint64_t *const p1 = nodes + c0 * stride;
-    const uint32_t q0 = pick4x<1>(m0, m1, m2, (uint32_t)a1, (uint32_t)b1, (uint32_t)c1n, (uint32_t)d1n);
-    const uint32_t q1 = pick4x<1>(m0, m1, m2, (uint32_t)(a1 >> 32), (uint32_t)(b1 >> 32), (uint32_t)(c1n >> 32),
+    const uint32_t q0 = pick4(m0, m1, m2, (uint32_t)a1, (uint32_t)b1, (uint32_t)c1n, (uint32_t)d1n);
+    const uint32_t q1 = pick4(m0, m1, m2, (uint32_t)(a1 >> 32), (uint32_t)(b1 >> 32), (uint32_t)(c1n >> 32),
                               (uint32_t)(d1n >> 32));
-    const uint32_t num1 = pick4x<1>(m0, m1, m2, num, e0, e1, e2);       // what is left of num below the child
-    const uint32_t below0 = pick4x<0>(m0, m1, m2, 0u, t0, t1, t2);
-    const uint32_t above0 = pick4x<0>(m0, m1, m2, t0, t1, t2, T);
+    const uint32_t num1 = pick4(m0, m1, m2, num, e0, e1, e2);       // what is left of num below the child
+    const uint32_t below0 = pick4(m0, m1, m2, 0u, t0, t1, t2);
+    const uint32_t above0 = pick4(m0, m1, m2, t0, t1, t2, T);
     root += 0x0001000100010000ull << (16u * c0);
     // level-2 candidates of that child
     uint64_t *const g2 = nodes + (4u + c0 * 4u) * stride;
@@ -624,15 +557,15 @@ GPUAR_HD uint32_t tree_decode_spec_range(uint64_t &root, uint64_t *nodes, uint32
     }
     uint64_t n2;
     if (kSpec & 2) {
-        const uint32_t lo2 = pick4x<2>(k0, k1, k2, (uint32_t)a2, (uint32_t)b2, (uint32_t)c2n, (uint32_t)d2n);
-        const uint32_t hi2 = pick4x<2>(k0, k1, k2, (uint32_t)(a2 >> 32), (uint32_t)(b2 >> 32), (uint32_t)(c2n >> 32),
+        const uint32_t lo2 = pick4(k0, k1, k2, (uint32_t)a2, (uint32_t)b2, (uint32_t)c2n, (uint32_t)d2n);
+        const uint32_t hi2 = pick4(k0, k1, k2, (uint32_t)(a2 >> 32), (uint32_t)(b2 >> 32), (uint32_t)(c2n >> 32),
                                    (uint32_t)(d2n >> 32));
         n2 = ((uint64_t)hi2 << 32) | lo2;
     } else {
         n2 = *p2;
     }
-    const uint32_t below1 = below0 + pick4x<0>(k0, k1, k2, 0u, u0, u1, u2);
-    const uint32_t above1 = pick4x<0>(k0, k1, k2, below0 + u0, below0 + u1, below0 + u2, above0);
+    const uint32_t below1 = below0 + pick4(k0, k1, k2, 0u, u0, u1, u2);
+    const uint32_t above1 = pick4(k0, k1, k2, below0 + u0, below0 + u1, below0 + u2, above0);
     *p1 = (((uint64_t)q1 << 32) | q0) + (0x0001000100010000ull << (16u * c1));
     // levels 2 and 3 on the quotient
     const uint32_t target = divide_exact(num, range);
@@ -643,8 +576,8 @@ GPUAR_HD uint32_t tree_decode_spec_range(uint64_t &root, uint64_t *nodes, uint32
         const uint32_t rr = rem * 0x10001u + 0x80008000u;
         const uint32_t dlo = rr - z0, dhi = rr - z1;               // bit 31 / 15: rem >= slot (tree_level)
         const uint32_t j0 = ~mask(dlo), j1 = ~mask(dhi << 16), j2 = ~mask(dhi);
-        const uint32_t lo3 = pick4x<3>(j0, j1, j2, (uint32_t)a3, (uint32_t)b3, (uint32_t)c3n, (uint32_t)d3n);
-        const uint32_t hi3 = pick4x<3>(j0, j1, j2, (uint32_t)(a3 >> 32), (uint32_t)(b3 >> 32), (uint32_t)(c3n >> 32),
+        const uint32_t lo3 = pick4(j0, j1, j2, (uint32_t)a3, (uint32_t)b3, (uint32_t)c3n, (uint32_t)d3n);
+        const uint32_t hi3 = pick4(j0, j1, j2, (uint32_t)(a3 >> 32), (uint32_t)(b3 >> 32), (uint32_t)(c3n >> 32),
                                    (uint32_t)(d3n >> 32));
         const uint32_t c2 = tree_level(n2, rem, room);
         *p2 = n2;
@@ -742,17 +675,8 @@ GPUAR_HD void enc_tree_init(uint64_t &root, uint64_t *nodes, uint32_t stride)
 
 // Node increments of the encoder (a constant-memory table of the four increments instead of the
 // variable 64-bit shift was measured: the per-lane index replays the LDC, slower everywhere).
-GPUAR_HD void add_halves(uint64_t &node, uint64_t inc)           // slots never carry into each other: two 32-bit adds
-{
-    if (GPUAR_FMA_ADDS & 1) {
-        const uint32_t lo = fadd<0>((uint32_t)node, (uint32_t)inc), hi = fadd<0>((uint32_t)(node >> 32), (uint32_t)(inc >> 32));
-        node = ((uint64_t)hi << 32) | lo;
-    } else {
-        node += inc;
-    }
-}
-GPUAR_HD void bump_above(uint64_t &node, uint32_t c) { add_halves(node, 0x0001000100010000ull << (16u * c)); }   // +1 on every slot above c
-GPUAR_HD void bump_at(uint64_t &node, uint32_t c) { add_halves(node, 1ull << (16u * c)); }                       // +1 on slot c
+GPUAR_HD void bump_above(uint64_t &node, uint32_t c) { node += 0x0001000100010000ull << (16u * c); }   // +1 on every slot above c
+GPUAR_HD void bump_at(uint64_t &node, uint32_t c) { node += 1ull << (16u * c); }                       // +1 on slot c
 
 GPUAR_HD uint32_t enc_upper(uint64_t &node, uint32_t c)   // slot c, then +1 above c
 {
@@ -768,7 +692,7 @@ GPUAR_HD uint32_t tree_encode_upper_at(uint64_t &root, uint64_t *node1, uint32_t
 {
     uint64_t n1 = *node1;
     uint32_t acc = enc_upper(root, c0);
-    acc = fadd<3>(acc, enc_upper(n1, c1));
+    acc += enc_upper(n1, c1);
     *node1 = n1;
     return acc;
 }
@@ -848,7 +772,7 @@ GPUAR_HD uint32_t tree_encode_lower(uint64_t *nodes, uint32_t stride, uint32_t s
     const uint32_t x = l * 0x10001u;                               // (n0, n0+n1)
     const uint32_t s01 = x >> 16;
     const uint32_t s012 = s01 + (h & 0xFFFFu);
-    acc = fadd<3>(acc, prmt(x << 16, s01 | (s012 << 16), 0x0010u + 0x0022u * c));
+    acc += prmt(x << 16, s01 | (s012 << 16), 0x0010u + 0x0022u * c);
     cnt = prmt(l, h, 0x3210u + 0x2222u * c) & 0xFFFFu;
     bump_at(n3, c);
     *p2 = n2;
@@ -859,7 +783,7 @@ GPUAR_HD uint32_t tree_encode_lower(uint64_t *nodes, uint32_t stride, uint32_t s
 GPUAR_HD void tree_encode(uint64_t &root, uint64_t *nodes, uint32_t stride, uint32_t s, uint32_t &lo, uint32_t &cnt)
 {
     const uint32_t up = tree_encode_upper(root, nodes, stride, s);
-    lo = fadd<3>(up, tree_encode_lower(nodes, stride, s, cnt));
+    lo = up + tree_encode_lower(nodes, stride, s, cnt);
 }
 
 // ---- funnel shifts (shf.l / shf.r.clamp) with host fall-backs

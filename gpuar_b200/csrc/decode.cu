@@ -22,9 +22,6 @@
 #include "common.cuh"
 #include "kernels.h"
 
-#ifndef GPUAR_DEC_BIG_MODE
-#define GPUAR_DEC_BIG_MODE -1       // tuning knob, register-feed variant: -1 = quotient first, then the plain tree;
-#endif                              // 0..7 = top levels decided by multiplication, bits = speculative loads (levels 1/2/3)
 #ifndef GPUAR_DEC_UNROLL
 #define GPUAR_DEC_UNROLL 4          // steps per unrolled block of the full-round loop (tuning knob)
 #endif
@@ -45,9 +42,6 @@ template <bool kRingFeed>
 struct DecShared {
     uint64_t tree[kTreeStored][32];          // 21504 B; lane l owns column l (banks 2l, 2l+1); root in registers
     uint32_t ring[kRingFeed ? kRing : 1][32];  // 1024 B stream ring (ring feed only: 21504 B keeps 10 CTAs per SM)
-#ifdef GPUAR_OCC_PAD
-    uint8_t pad[GPUAR_OCC_PAD];                // occupancy experiment: fewer CTAs per SM
-#endif
 };
 
 // 4-byte asynchronous global->shared copy (LDGSTS): no register, no scoreboard -- the stream
@@ -159,10 +153,10 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     auto step = [&](uint32_t i, uint32_t m, uint32_t sh, uint32_t slot) {
         const uint32_t T = 256u + i;
         uint32_t lo, cnt;
-        uint32_t s;
-        if (kRingFeed) s = tree_decode_early_range(root, tree, 32u, code, L, R, T, lo, cnt);
-        else if (GPUAR_DEC_BIG_MODE >= 0) s = tree_decode_early_range<(GPUAR_DEC_BIG_MODE < 0 ? 0 : GPUAR_DEC_BIG_MODE)>(root, tree, 32u, code, L, R, T, lo, cnt);
-        else s = tree_decode(root, tree, 32u, unscale_range(code, L, R, T), T, lo, cnt);
+        // latency variant: top levels decided by multiplication with speculative node loads; throughput variant: the
+        // quotient first, then the plain tree (the other way round was measured on both, profiles/r2_kernel_experiments.md)
+        const uint32_t s = kRingFeed ? tree_decode_early_range(root, tree, 32u, code, L, R, T, lo, cnt)
+                                     : tree_decode(root, tree, 32u, unscale_range(code, L, R, T), T, lo, cnt);
         packed |= s << (8u * slot);
         uint32_t L1, S1, t, As;
         narrow_total(L, R, lo, lo + cnt, m, sh, L1, S1, t, As);

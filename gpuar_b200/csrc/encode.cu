@@ -33,9 +33,6 @@ namespace gpuar {
 // ------------------------------------------------------------------ encode
 struct EncShared {
     uint64_t tree[kTreeStored][32];  // 21504 B; lane l owns column l (banks 2l, 2l+1); root in registers
-#ifdef GPUAR_OCC_PAD
-    uint8_t pad[GPUAR_OCC_PAD];      // occupancy experiment: fewer CTAs per SM
-#endif
 };
 
 __global__ void __launch_bounds__(32)
