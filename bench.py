@@ -570,7 +570,7 @@ def measure(rig, workload, steps, warmup, sampler=None, with_cpu_baseline=False)
         del out
         out = None
     torch.cuda.empty_cache()
-    t_e2e_enc = t_e2e_dec = t_link = 0.0
+    t_e2e_enc = t_e2e_dec = t_link = t_link_dec = 0.0
     gip_bytes = 0
     host_n = n if world == 1 else job
     devices = None if world == 1 else list(range(world))
@@ -611,6 +611,12 @@ def measure(rig, workload, steps, warmup, sampler=None, with_cpu_baseline=False)
         for _ in range(e2e_steps):
             codec.link_probe(np_in, np_out, gip_bytes - 20, devices=devices)
         t_link = (time.perf_counter() - t0) / e2e_steps
+        # ... and of the decode direction: the image up, the raw bytes down
+        codec.link_probe(g, np_out, host_n, devices=devices)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            codec.link_probe(g, np_out, host_n, devices=devices)
+        t_link_dec = (time.perf_counter() - t0) / e2e_steps
         del host_in, host_gip, host_out, np_in, np_gip, np_out, g, back
     rig.host_barrier()
 
@@ -643,7 +649,9 @@ def measure(rig, workload, steps, warmup, sampler=None, with_cpu_baseline=False)
                                              "same streams, no kernels (PCIe links + host memory for this pattern)"}},
             "e2e_decode": {"value": job / t_e2e_dec / GB, "unit": "GB/s", "h2d_bytes_per_step": gip_bytes - 20,
                            "d2h_bytes_per_step": host_n,
-                           "api": "gpuar_b200_decompress_host" if world == 1 else "gpuar_b200_decompress_host_multi"},
+                           "api": "gpuar_b200_decompress_host" if world == 1 else "gpuar_b200_decompress_host_multi",
+                           "link_ceiling": {"value": job / t_link_dec / GB, "unit": "GB/s",
+                                            "what": "gpuar_b200_host_link_probe with the image going up and the raw bytes coming down"}},
             "parity": parity,
             "gpu_launches": launches,
             "kernels_ms_per_step": {k: per(k) for k in spans},

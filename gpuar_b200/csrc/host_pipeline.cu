@@ -244,12 +244,12 @@ static int link_probe_on(Crew &crew, const uint8_t *in, size_t n, uint8_t *out, 
         if ((e = cudaSetDevice(h.device)) != cudaSuccess) break;
         if (l.used) e = cudaStreamWaitEvent(h.up, l.drained, 0);       // the lane's buffers are still on their way down
         if (e == cudaSuccess) e = l.in.need(align_up_h(m, 16) + 16);
-        if (e == cudaSuccess) e = l.out.need(gpuar_b200_payload_bound(m) + 16);
+        if (e == cudaSuccess) e = l.out.need((down > gpuar_b200_payload_bound(m) ? down : gpuar_b200_payload_bound(m)) + 16);
         if (e != cudaSuccess) break;
         e = cudaMemcpyAsync(l.in.p, in + off, m, cudaMemcpyHostToDevice, h.up);
         if (e == cudaSuccess) e = cudaEventRecord(l.arrived, h.up);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(h.down, l.arrived, 0);
-        if (e == cudaSuccess && down) e = cudaMemcpyAsync(out + pos, l.out.p, down < l.out.cap ? down : l.out.cap, cudaMemcpyDeviceToHost, h.down);
+        if (e == cudaSuccess && down) e = cudaMemcpyAsync(out + pos, l.out.p, down, cudaMemcpyDeviceToHost, h.down);
         if (e == cudaSuccess) e = cudaEventRecord(l.drained, h.down);
         l.used = true;
         pos += down;
