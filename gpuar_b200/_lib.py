@@ -79,6 +79,7 @@ SIGNATURES = {
     "gpuar_b200_set_option": (C.c_int, [C.c_int, C.c_longlong]),
     "gpuar_b200_profile": (None, [C.c_int]),
     "gpuar_b200_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "gpuar_b200_selfcheck": (C.c_int, [C.POINTER(C.c_uint64)]),
     "gpuar_b200_launch_count": (C.c_uint64, []),
 }
 
@@ -122,7 +123,7 @@ def check(code: int, what: str) -> None:
         raise GpuarError(code, what)
 
 
-OPT_ENCODE_PATH, OPT_WS_MAX_PACKETS, OPT_COMPACT_TILE = 1, 2, 3
+OPT_ENCODE_PATH, OPT_WS_MAX_PACKETS, OPT_COMPACT_TILE, OPT_DECODE_PATH = 1, 2, 3, 4
 ENCODE_AUTO, ENCODE_FUSED, ENCODE_WS = 0, 1, 2
 
 
@@ -143,6 +144,13 @@ def profile_read() -> dict:
     calls = (C.c_uint64 * 4)()
     check(lib().gpuar_b200_profile_read(ms, calls), "gpuar_b200_profile_read")
     return {name: (float(ms[k]), int(calls[k])) for k, name in enumerate(SPANS)}
+
+
+def selfcheck() -> int:
+    """Mismatches of the device self-check of the decoder's quotient (0 = it holds everywhere)."""
+    bad = C.c_uint64(1)
+    check(lib().gpuar_b200_selfcheck(C.byref(bad)), "gpuar_b200_selfcheck")
+    return int(bad.value)
 
 
 def launch_count() -> int:

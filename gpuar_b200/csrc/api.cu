@@ -274,6 +274,8 @@ int gpuar_b200_set_option(int key, long long value)
     case GPUAR_OPT_COMPACT_TILE:
         if (value < 0 || value > 128 || !set_compact_tile((uint32_t)value)) return GPUAR_E_ARG;
         return 0;
+    case GPUAR_OPT_DECODE_PATH:
+        return set_decode_path((int)value) && value == (int)value ? 0 : GPUAR_E_ARG;
     default:
         return GPUAR_E_ARG;
     }
@@ -297,6 +299,18 @@ int gpuar_b200_profile_read(double ms[GPUAR_SPAN_COUNT], uint64_t calls[GPUAR_SP
     }
     g_spans.clear();
     return ck(bad);
+}
+
+int gpuar_b200_selfcheck(uint64_t *mismatches)
+{
+    if (!mismatches) return GPUAR_E_ARG;
+    uint64_t *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(uint64_t));
+    if (e != cudaSuccess) return ck(e);
+    e = launch_selfcheck(d, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(mismatches, d, sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return ck(e);
 }
 
 /* ------------------------------------------------------------------ header */

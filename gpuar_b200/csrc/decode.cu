@@ -7,19 +7,21 @@
 // Fenwick sums + update) and readEncodedBits (:787-836, bit-at-a-time).
 //
 // Here the adaptive model of each packet is a 4-ary cumulative-count tree in shared
-// memory, interleaved so that lane l only ever touches bank pair (2l, 2l+1):
+// memory, interleaved so that lane l only ever touches its own banks:
 //   level 0: 1 node  (children span 64 symbols)      node = four u16 slots (0, t0, t1, t2):
 //   level 1: 4 nodes (16)                            t0 = |child0|, t1 = t0+|child1|,
 //   level 2: 16 nodes (4)                            t2 = t1+|child2|
-//   level 3: 64 nodes (1)
+//   level 3: 64 leaves (1)                           leaf = inclusive prefix sums (s0, s1, s2, s3)
 // One branch-free descent (root in registers, then 3 dependent 8-byte shared loads) finds
-// the symbol, yields cum[s] and count[s] and applies the model update (+1 on every slot
-// right of the path) in the same pass (coder_math.h: tree_level).  Interval arithmetic and
-// renormalisation are the single-normalisation step of coder_math.h (narrow_total: state =
-// lower bound and range); bits come from a 64-bit reservoir fed by 32-bit words.
+// the symbol, yields cum[s] and cum[s+1] and applies the model update (+1 on every slot
+// right of the path) in the same pass.  The symbol step itself -- quotient, descent, interval
+// narrowing with its single normalisation, next bits -- is decode_math.h (decode_step for the
+// throughput variant, decode_step_latency for the latency variant; state = code - lower bound,
+// lower bound, range); bits come from a 64-bit reservoir fed by 32-bit words.
 #include <cstdlib>
 
 #include "common.cuh"
+#include "decode_math.h"
 #include "kernels.h"
 
 #ifndef GPUAR_DEC_UNROLL
@@ -38,10 +40,22 @@ __device__ __forceinline__ const uint32_t *clamp_ptr(const uint32_t *p, const ui
 constexpr uint32_t kRing = 8;        // per-lane ring of stream words in shared memory
 constexpr uint32_t kAhead = 3;       // words requested ahead of the reader
 
+#ifndef GPUAR_DEC_SPEC2
+#define GPUAR_DEC_SPEC2 7           // tuning knob: speculative node loads of the latency variant (decode_math.h)
+#endif
+
 template <bool kRingFeed>
-struct DecShared {
-    uint64_t tree[kTreeStored][32];          // 21504 B; lane l owns column l (banks 2l, 2l+1); root in registers
-    uint32_t ring[kRingFeed ? kRing : 1][32];  // 1024 B stream ring (ring feed only: 21504 B keeps 10 CTAs per SM)
+struct DecShared;
+template <>
+struct DecShared<false> {                    // throughput variant: 21504 B keeps 10 CTAs per SM
+    uint64_t tree[kTreeStored][32];          // lane l owns column l (banks 2l, 2l+1); root in registers
+};
+template <>
+struct DecShared<true> {                     // latency variant (at most 4 CTAs per SM: size does not matter)
+    Quad l1[4][32];                          // level-1 thresholds as 32-bit words (16 B per lane and node)
+    uint64_t l2[16][32];
+    uint64_t l3[64][32];
+    uint32_t ring[kRing][32];                // 1024 B stream ring
 };
 
 // 4-byte asynchronous global->shared copy (LDGSTS): no register, no scoreboard -- the stream
@@ -77,9 +91,17 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     const bool mine = my < n_packets;
 
     // model init: every count 1 (gpuar_kernel.cu:403-419)
-    uint64_t *const tree = &sm.tree[0][lane];
-    uint64_t root;
-    tree_init(root, tree, 32u);
+    uint64_t root = 0;
+    uint32_t T0 = 0, T1 = 0, T2 = 0;             // latency variant: the root's thresholds
+    uint64_t *tree = nullptr;
+    LatTree lat{nullptr, nullptr, nullptr, 32u};
+    if constexpr (kRingFeed) {
+        lat = LatTree{&sm.l1[0][lane], &sm.l2[0][lane], &sm.l3[0][lane], 32u};
+        lat_tree_init(T0, T1, T2, lat);
+    } else {
+        tree = &sm.tree[0][lane];
+        dec_tree_init(root, tree, 32u);
+    }
 
     // bit source: aligned 32-bit words of the packet's bitstream.  The window is fed from a
     // per-lane ring in shared memory that cp.async keeps kAhead words ahead of the reader.
@@ -108,7 +130,8 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     // and 32-bit index arithmetic do (a 64-bit pointer to bump and clamp costs four instructions more)
     const uint32_t *const g0 = clamp_ptr(gp, wend);
     const uint32_t p_max = (uint32_t)min((ptrdiff_t)(wend - g0), (ptrdiff_t)0x3FFFFFFF);
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(&sm.ring[0][lane]);
+    uint32_t ring_s = 0;
+    if constexpr (kRingFeed) ring_s = (uint32_t)__cvta_generic_to_shared(&sm.ring[0][lane]);
     auto request = [&](uint32_t p) {
         const uint32_t dst = ring_s + ((p & (kRing - 1u)) << 7);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(g0 + min(p, p_max)) : "memory");
@@ -122,7 +145,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     }
     auto refill = [&]() {
         if (kRingFeed) {
-            // One refill per step, predicated, never divergent: feed the ring's next word if the
+            // One refill per two steps (below), predicated, never divergent: feed the ring's next word if the
             // window has room, and request one more word.  A word is read at least kAhead steps
             // after it was requested, so waiting for all but the kAhead-1 newest groups makes it
             // visible.
@@ -140,10 +163,12 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
             ahead = *clamp_ptr(gp, wend);
         }
     };
-    // initializeDecoder (:582-603): the first 16 bits
-    uint32_t code = in.take(16u);
+    // initializeDecoder (:582-603): the first 16 bits; lower bound 0, range 2^16
+    DecState st;
+    st.D = in.take(16u);
+    st.L = 0;
+    st.R = 65536u;
     refill();
-    uint32_t L = 0, R = 65536u;                     // narrow_total state: lower bound and range
 
     const uint32_t max_raw = __reduce_max_sync(kFull, raw);
     uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)my * packet);
@@ -152,16 +177,15 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     // one symbol of this lane's packet; `slot` = position of the byte inside the 32-bit store word
     auto step = [&](uint32_t i, uint32_t m, uint32_t sh, uint32_t slot) {
         const uint32_t T = 256u + i;
-        uint32_t lo, cnt;
         // latency variant: top levels decided by multiplication with speculative node loads; throughput variant: the
         // quotient first, then the plain tree (the other way round was measured on both, profiles/r2_kernel_experiments.md)
-        const uint32_t s = kRingFeed ? tree_decode_early_range(root, tree, 32u, code, L, R, T, lo, cnt)
-                                     : tree_decode(root, tree, 32u, unscale_range(code, L, R, T), T, lo, cnt);
-        packed |= s << (8u * slot);
-        uint32_t L1, S1, t, As;
-        narrow_total(L, R, lo, lo + cnt, m, sh, L1, S1, t, As);
-        code = advance_code_total(code, t, As, in);
-        refill();
+        uint32_t s;
+        if constexpr (kRingFeed) s = decode_step_latency<GPUAR_DEC_SPEC2>(st, T0, T1, T2, lat, T, m, sh, in);
+        else s = decode_step(st, root, tree, 32u, T, m, sh, in);
+        packed = mad32(s, 1u << (8u * slot), packed);               // fields cannot overlap: a multiply-add, not shift + or
+        // A step takes at most 16 bits and the window holds at least 33 after a refill: one refill (at most one
+        // word) every SECOND step keeps at least 17 bits in front of every step and restores 33.
+        if (slot & 1u) refill();
     };
 
     const uint32_t min_raw = __reduce_min_sync(kFull, mine ? raw : packet);
@@ -203,6 +227,42 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     }
 }
 
+// Device self-check of the decoder's float-estimated quotient (decode_math.h: divide_floor): every range the
+// coder can hold (2^14 < range <= 2^16), every quotient up to 2^14 - 1, numerators at both ends and in the
+// middle of each quotient's interval.  The approximate reciprocal only exists on the device, so this is where
+// the one-sided correction is pinned (the host model checks the same lattice with a divide in its place).
+__global__ void __launch_bounds__(256)
+selfcheck_divide_kernel(unsigned long long *__restrict__ bad)
+{
+    const uint32_t range = 16385u + blockIdx.x;
+    unsigned long long n = 0;
+    for (uint32_t q = threadIdx.x; q < 16384u; q += blockDim.x) {
+        const uint32_t base = q * range;                            // (q + 1) * range - 1 < 2^30
+        n += divide_floor(base, range) != q;
+        n += divide_floor(base + (range >> 1), range) != q;
+        n += divide_floor(base + range - 1u, range) != q;
+        n += divide_exact(base + range - 1u, range) != q;
+    }
+    if (n) atomicAdd(bad, n);
+}
+
+cudaError_t launch_selfcheck(uint64_t *d_mismatches, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(d_mismatches, 0, sizeof(uint64_t), st);
+    if (e != cudaSuccess) return e;
+    selfcheck_divide_kernel<<<65536u - 16384u, 256, 0, st>>>(reinterpret_cast<unsigned long long *>(d_mismatches));
+    count_launch();
+    return cudaGetLastError();
+}
+
+static int g_decode_path = 0;        // 0 auto, 1 latency variant, 2 throughput variant
+bool set_decode_path(int path)
+{
+    if (path < 0 || path > 2) return false;
+    g_decode_path = path;
+    return true;
+}
+
 cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint64_t *d_offsets, uint32_t stride,
                           uint32_t packets, uint8_t *d_out, uint32_t packet, cudaStream_t st, const uint64_t *d_count)
 {
@@ -211,13 +271,14 @@ cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint6
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t grid = (packets + 31u) / 32u;
-    // tuning aid: GPUAR_B200_DEC_RING_MAX=<CTAs> moves the switch between the two variants
+    // The latency-optimised variant pays for its short chain with more instructions per step.  It wins while
+    // every warp has a scheduler to itself (4 per SM) and loses as soon as two warps share one
+    // (profiles/r1_s2_dec_switch.txt, profiles/r2_decode_v2.md).  GPUAR_OPT_DECODE_PATH forces one of them
+    // (tests run both on the same streams); GPUAR_B200_DEC_RING_MAX=<CTAs> moves the switch (tuning aid).
     static const long forced = [] { const char *e = getenv("GPUAR_B200_DEC_RING_MAX"); return e && *e ? atol(e) : -1L; }();
-    // The latency-optimised variant pays for its short chain with 246 instructions per step (the
-    // other one: 177).  It wins while every warp has a scheduler to itself (4 per SM: 1.67 against
-    // 2.55 ms at 128 MiB) and loses as soon as two warps share one (2.95 against 2.72 ms at 192 MiB,
-    // 4.41 against 3.30 ms at 368 MiB; profiles/r1_s2_dec_switch.txt).
-    const uint32_t ring_max = forced >= 0 ? (uint32_t)forced : (uint32_t)sms * 4u;
+    uint32_t ring_max = forced >= 0 ? (uint32_t)forced : (uint32_t)sms * 4u;
+    if (g_decode_path == 1) ring_max = 0xFFFFFFFFu;
+    if (g_decode_path == 2) ring_max = 0u;
     if (grid <= ring_max)
         decode_kernel<true><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet, d_count);
     else

@@ -53,6 +53,11 @@ cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint6
                           uint32_t packets, uint8_t *d_out, uint32_t packet, cudaStream_t st,
                           const uint64_t *d_count = nullptr);
 
+bool set_decode_path(int path);    // 0 auto (by packet count), 1 latency variant, 2 throughput variant
+
+// device self-check of the decoder's closed forms (decode.cu): *d_mismatches = 0 when they all hold
+cudaError_t launch_selfcheck(uint64_t *d_mismatches, cudaStream_t st);
+
 // index.cu
 // sizes[p] = min(rawLen of the packet at d_offsets[p], packet): what decode writes for packet p
 cudaError_t launch_raw_sizes(const uint8_t *d_payload, size_t c, const uint64_t *d_offsets, uint32_t packets,

@@ -284,6 +284,9 @@ void garDecompressExecutor(const uint8_t *source, size_t size, uint8_t *destinat
 #define GPUAR_OPT_WS_MAX_PACKETS 2   /* auto: use the warp-specialised kernel up to this many packets */
 #define GPUAR_OPT_COMPACT_TILE 3     /* packets per work unit of the scan + compaction kernel: 0 auto (default),
                                         or a power of two 4..128 (32 KiB .. 1 MiB of input per CTA) */
+#define GPUAR_OPT_DECODE_PATH 4      /* decode kernel: 0 auto (default: by packet count), 1 latency variant
+                                        (speculative node loads, for inputs that leave warp schedulers idle),
+                                        2 throughput variant */
 int gpuar_b200_set_option(int key, long long value);
 
 /* ----------------------------------------------------------- measurement hooks
@@ -297,6 +300,12 @@ int gpuar_b200_set_option(int key, long long value);
 #define GPUAR_SPAN_COUNT 4
 void gpuar_b200_profile(int enable);
 int gpuar_b200_profile_read(double ms[GPUAR_SPAN_COUNT], uint64_t calls[GPUAR_SPAN_COUNT]);
+
+/* Device self-check of the decoder's float-estimated quotient (the decoder's replacement for the division
+ * of getUnscaledCode, src/gpuar_kernel.cu:703-716): every range the coder can hold, every quotient, both
+ * ends of each quotient's interval, on the current device (the approximate reciprocal it is built on only
+ * exists there).  *mismatches = 0 when it holds everywhere.  A test hook; ~20 ms. */
+int gpuar_b200_selfcheck(uint64_t *mismatches);
 
 /* launch counter: number of this library's kernels launched since load (bench.py's gpu_launches) */
 uint64_t gpuar_b200_launch_count(void);

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../gpuar_b200/csrc/coder_math.h"
+#include "../gpuar_b200/csrc/decode_math.h"
 
 using namespace gpuar;
 
@@ -171,6 +172,54 @@ uint32_t host_model_decode_packet_total(const uint8_t *payload, size_t readable,
     return decode_packet(payload, readable, off, out, early != 0, true);
 }
 
+// the second-generation decoder step (decode_math.h) exactly as a lane of decode_kernel runs it:
+// variant 0 = throughput (decode_step), 1..4 = latency (decode_step_latency<7 / 5 / 3 / 1>)
+uint32_t host_model_decode_packet_v2(const uint8_t *payload, size_t readable, size_t off, uint8_t *out, int variant)
+{
+    std::vector<uint64_t> tree(kTreeStored);
+    std::vector<Quad> l1(4);
+    uint64_t root = 0;
+    uint32_t T0 = 0, T1 = 0, T2 = 0;
+    LatTree tr{l1.data(), tree.data() + 4, tree.data() + 20, 1u};
+    if (variant == 0) dec_tree_init(root, tree.data(), 1);
+    else lat_tree_init(T0, T1, T2, tr);
+    const uint32_t *const words = reinterpret_cast<const uint32_t *>(payload);
+    const uint32_t *const wend = words + (readable >> 2) - 1;
+    auto word = [&](const uint32_t *p) { return bswap32(*(p < wend ? p : wend)); };
+    const uint32_t raw = (uint32_t)payload[off + 2] | ((uint32_t)payload[off + 3] << 8);
+    const size_t sp = off + kHdr;
+    const uint32_t *wp = words + (sp >> 2);
+    const uint32_t skip = 8u * (uint32_t)(sp & 3u);
+    BitSource in;
+    const uint64_t w0 = word(wp);
+    ++wp;
+    const uint64_t w1 = word(wp);
+    ++wp;
+    in.start(((w0 << 32) | w1) << skip, 64u - skip);
+    uint32_t ahead = word(wp);
+    DecState st;
+    st.D = in.take(16u);
+    st.L = 0;
+    st.R = 65536u;
+    if (in.hungry()) { in.feed(ahead); ++wp; ahead = word(wp); }
+    for (uint32_t i = 0; i < raw; ++i) {
+        const uint32_t T = 256u + i;
+        uint32_t sh;
+        const uint32_t m = magic_for(T, sh);
+        uint32_t s;
+        switch (variant) {
+        case 0: s = decode_step(st, root, tree.data(), 1, T, m, sh, in); break;
+        case 1: s = decode_step_latency<7>(st, T0, T1, T2, tr, T, m, sh, in); break;
+        case 2: s = decode_step_latency<5>(st, T0, T1, T2, tr, T, m, sh, in); break;
+        case 3: s = decode_step_latency<3>(st, T0, T1, T2, tr, T, m, sh, in); break;
+        default: s = decode_step_latency<1>(st, T0, T1, T2, tr, T, m, sh, in); break;
+        }
+        out[i] = (uint8_t)s;
+        if (in.hungry()) { in.feed(ahead); ++wp; ahead = word(wp); }
+    }
+    return raw;
+}
+
 // exhaustive-ish check of the reciprocal division: for every total T and for numerators
 // around every multiple of T up to max_n (plus random ones): returns the number of mismatches
 uint64_t host_model_check_division(uint32_t max_n, uint32_t packet)
@@ -253,6 +302,7 @@ uint64_t host_model_check_unscale(uint32_t stride, uint32_t packet)
                 const uint32_t L = 0, V = 65536u - range, code = cl;
                 const uint32_t want = ((cl + 1u) * T - 1u) / range;
                 bad += unscale(code, L, V, T) != want;
+                bad += divide_floor((cl + 1u) * T - 1u, range) != want;
             }
     return bad;
 }

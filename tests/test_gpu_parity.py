@@ -199,6 +199,30 @@ def test_decode_ragged_sizes(dev, n):
     assert np.array_equal(got, data)
 
 
+@pytest.mark.parametrize("path", ["latency", "throughput"])
+def test_both_decode_kernels_are_bit_exact(dev, path):
+    # the two decode kernels (decode_math.h: decode_step_latency / decode_step) on the same streams: golden
+    # vectors made by the reference, ragged tails, a long-underflow stream, one-symbol packets
+    from gpuar_b200 import _lib
+    rng = np.random.default_rng(11)
+    cases = [make_input(VECTORS[name]) for name in SMALL]
+    cases += [D.mixed(5, 8192 * 70 + 123), D.zeros(8192 * 3 + 1), D.uniform(9, 8192 * 40 - 1),
+              rng.choice(np.array([127, 128], np.uint8), size=8192 * 33)]
+    _lib.set_option(_lib.OPT_DECODE_PATH, {"latency": 1, "throughput": 2}[path])
+    try:
+        for data in cases:
+            got = dev.decode_bytes(to_dev(O.encode(data))).cpu().numpy()
+            assert np.array_equal(got, data)
+    finally:
+        _lib.set_option(_lib.OPT_DECODE_PATH, 0)
+
+
+def test_device_selfcheck_of_the_quotient():
+    # divide_floor (one-sided float estimate) over every range and quotient, on the device
+    from gpuar_b200 import _lib
+    assert _lib.selfcheck() == 0
+
+
 # ------------------------------------------------------------ host-buffer path
 @pytest.mark.parametrize("name", ["one", "short", "maintest", "u8193", "m96k", "m1m", "u1m_tail"])
 def test_gip_image_equals_reference_under_header_mask(codec, name):

@@ -19,8 +19,8 @@ SO = os.path.join(HERE, "_build", "libhost_model.so")
 @pytest.fixture(scope="module")
 def model():
     src = os.path.join(HERE, "host_model.cpp")
-    hdr = os.path.join(HERE, "..", "gpuar_b200", "csrc", "coder_math.h")
-    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(HERE, "..", "gpuar_b200", "csrc", h) for h in ("coder_math.h", "decode_math.h")]
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(f) for f in [src] + hdrs):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", src, "-o", SO])
     lib = C.CDLL(SO)
@@ -34,6 +34,8 @@ def model():
     lib.host_model_decode_packet_early.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p]
     lib.host_model_decode_packet_total.restype = C.c_uint32
     lib.host_model_decode_packet_total.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p, C.c_int]
+    lib.host_model_decode_packet_v2.restype = C.c_uint32
+    lib.host_model_decode_packet_v2.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p, C.c_int]
     lib.host_model_check_division.restype = C.c_uint64
     lib.host_model_check_division.argtypes = [C.c_uint32, C.c_uint32]
     lib.host_model_check_renorm.restype = C.c_uint64
@@ -50,8 +52,11 @@ def model_encode(lib, data, packet=8192, ws=False):
     return buf[: fn(O._ptr(src), data.size, O._ptr(buf), packet)].copy()
 
 
-def model_decode(lib, pay, n, early=False, total=False):
+def model_decode(lib, pay, n, early=False, total=False, v2=None):
     fn = lib.host_model_decode_packet_early if early else lib.host_model_decode_packet
+    if v2 is not None:                     # decode_math.h: 0 = throughput step, 1..4 = latency step
+        def fn(p, r, o, out):
+            return lib.host_model_decode_packet_v2(p, r, o, out, v2)
     if total:
         def fn(p, r, o, out, _early=int(early)):
             return lib.host_model_decode_packet_total(p, r, o, out, _early)
@@ -94,6 +99,8 @@ def test_kernel_math_matches_reference_golden(model, name):
     assert np.array_equal(model_decode(model, pay, data.size, early=True), data)
     assert np.array_equal(model_decode(model, pay, data.size, early=True, total=True), data)
     assert np.array_equal(model_decode(model, pay, data.size, total=True), data)
+    for v in range(5):
+        assert np.array_equal(model_decode(model, pay, data.size, v2=v), data)
 
 
 @pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 63, 64, 65, 4095, 8191, 8192])
@@ -106,6 +113,8 @@ def test_kernel_math_ragged_lengths(model, n):
         assert np.array_equal(model_decode(model, pay, n, early=True), data)
         assert np.array_equal(model_decode(model, pay, n, early=True, total=True), data)
         assert np.array_equal(model_decode(model, pay, n, total=True), data)
+        for v in range(5):
+            assert np.array_equal(model_decode(model, pay, n, v2=v), data)
 
 
 @pytest.mark.parametrize("packet", [4096, 12288, 16112])
@@ -120,6 +129,8 @@ def test_kernel_math_other_packet_sizes(model, packet):
     assert np.array_equal(model_decode(model, pay, data.size, early=True), data)
     assert np.array_equal(model_decode(model, pay, data.size, early=True, total=True), data)
     assert np.array_equal(model_decode(model, pay, data.size, total=True), data)
+    for v in range(5):
+        assert np.array_equal(model_decode(model, pay, data.size, v2=v), data)
 
 
 def test_kernel_math_long_underflow_runs(model):
@@ -132,3 +143,5 @@ def test_kernel_math_long_underflow_runs(model):
         assert np.array_equal(model_encode(model, data, ws=True), pay)
         assert np.array_equal(model_decode(model, pay, 8192), data)
         assert np.array_equal(model_decode(model, pay, 8192, early=True, total=True), data)
+        for v in range(5):
+            assert np.array_equal(model_decode(model, pay, 8192, v2=v), data)

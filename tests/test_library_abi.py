@@ -90,7 +90,8 @@ def test_options_validate_their_values():
     """gpuar_b200_set_option: unknown keys and out-of-range values are refused (no device needed)."""
     for key, good, bad in ((_lib.OPT_ENCODE_PATH, (0, 1, 2), (-1, 3)),
                            (_lib.OPT_COMPACT_TILE, (4, 8, 16, 32, 64, 128, 0), (-4, 2, 3, 24, 256)),
-                           (_lib.OPT_WS_MAX_PACKETS, (0, 23680), (-1,))):
+                           (_lib.OPT_WS_MAX_PACKETS, (0, 23680), (-1,)),
+                           (_lib.OPT_DECODE_PATH, (1, 2, 0), (-1, 3, 1 << 32))):
         for v in bad:
             assert _lib.lib().gpuar_b200_set_option(key, v) == _lib.E_ARG, (key, v)
         for v in good:
