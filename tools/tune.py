@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--gen", default="uniform", choices=["uniform", "and3", "mixed"])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--decode", action="store_true")
+    ap.add_argument("--dec-paths", default="0", help="GPUAR_OPT_DECODE_PATH values to time (0 auto, 1 latency, 2 throughput, 3 latency without the quotient)")
     args = ap.parse_args()
     dev = codec.DeviceCodec(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -62,10 +63,14 @@ def main():
                     packets = (n + 8191) // 8192
                     off, res = dev.index(payload, c, packets)
                     out = torch.empty(packets * 8192, dtype=torch.uint8, device="cuda")
-                    rec = spans(lambda: (dev.index(payload, c, packets, off, res),
-                                         dev.decode(payload, c, off, packets, out)), args.reps, flush)
-                    assert torch.equal(out[:n], x)
-                    line.update(rec)
+                    for dp in (int(v) for v in args.dec_paths.split(",")):
+                        _lib.set_option(_lib.OPT_DECODE_PATH, dp)
+                        out.zero_()
+                        rec = spans(lambda: (dev.index(payload, c, packets, off, res),
+                                             dev.decode(payload, c, off, packets, out)), args.reps, flush)
+                        assert torch.equal(out[:n], x)
+                        line.update(rec if dp == 0 else {f"decode_path{dp}": rec["decode"]})
+                    _lib.set_option(_lib.OPT_DECODE_PATH, 0)
                 print(json.dumps(line), flush=True)
         _lib.set_option(_lib.OPT_ENCODE_PATH, 0)
         _lib.lib().gpuar_b200_set_option(_lib.OPT_COMPACT_TILE, 0)

@@ -18,6 +18,9 @@ __global__ void __launch_bounds__(32) probe(uint32_t *out, uint64_t *cycles, uin
     uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 * 5u, a3 = a0 * 7u, a4 = a0 * 11u, a5 = a0 * 13u,
              a6 = a0 * 17u, a7 = a0 * 19u;
     uint32_t b = seed | 1u, c = seed * 77u + 5u;
+    __shared__ uint32_t sm[32];
+    sm[threadIdx.x] = (threadIdx.x * 7u + seed) & 31u;
+    __syncwarp();
     const uint64_t t0 = clock64();
 #pragma unroll 1
     for (int i = 0; i < kIters; ++i) {
@@ -87,6 +90,51 @@ __global__ void __launch_bounds__(32) probe(uint32_t *out, uint64_t *cycles, uin
 #define OP(x) asm volatile("mad.lo.u32 %0, %0, 65537, %1;" : "+r"(x) : "r"(c));
             CHAINS8(OP) CHAINS8(OP)
 #undef OP
+        } else if (kTest == 20) {   // dependent chain through a predicate: ISETP -> SEL
+#define OP(x) asm volatile("{.reg .pred p; setp.lt.s32 p, %0, %1; selp.u32 %0, %2, %1, p; xor.b32 %0, %0, %1;}" : "+r"(a0) : "r"(b), "r"(c));
+            CHAINS8(OP)
+#undef OP
+        } else if (kTest == 21) {   // the same decision on a sign mask: SHF -> LOP3
+#define OP(x) asm volatile("{.reg .u32 t; shr.s32 t, %0, 31; lop3.b32 %0, %2, t, %1, 0xd8; xor.b32 %0, %0, %1;}" : "+r"(a0) : "r"(b), "r"(c));
+            CHAINS8(OP)
+#undef OP
+        } else if (kTest == 22) {   // one tree level on predicates: IMAD -> ISETP -> SEL -> SEL
+#define OP(x) asm volatile("{.reg .pred p, q; .reg .u32 t, u; mad.lo.u32 t, %0, %1, %2; setp.lt.s32 p, t, 0; add.u32 u, t, %1; setp.lt.s32 q, u, 0; selp.u32 t, %1, %2, p; @q selp.u32 t, %2, %0, p; mov.u32 %0, t;}" : "+r"(a0) : "r"(b), "r"(c));
+            CHAINS8(OP)
+#undef OP
+        } else if (kTest == 23) {   // one tree level on masks: IMAD -> SHF -> LOP3 -> LOP3
+#define OP(x) asm volatile("{.reg .u32 t, u, v; mad.lo.u32 t, %0, %1, %2; shr.s32 u, t, 31; lop3.b32 v, %1, u, %2, 0xd8; lop3.b32 %0, v, u, %0, 0xd8;}" : "+r"(a0) : "r"(b), "r"(c));
+            CHAINS8(OP)
+#undef OP
+        } else if (kTest == 24) {   // quotient chain: I2F -> FMUL -> F2I
+#define OP(x) asm volatile("{.reg .f32 f; cvt.rz.f32.u32 f, %0; mul.f32 f, f, %1; cvt.rzi.u32.f32 %0, f;}" : "+r"(a0) : "f"(1.0001f));
+            CHAINS8(OP)
+#undef OP
+        } else if (kTest == 25) {   // dependent IMAD.HI
+#define OP(x) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a0) : "r"(0xFFFFFFF0u));
+            CHAINS8(OP) CHAINS8(OP)
+#undef OP
+        } else if (kTest == 26) {   // dependent FADD
+#define OP(x) asm volatile("add.f32 %0, %0, %1;" : "+f"(*(float *)&a0) : "f"(1.5f));
+            CHAINS8(OP) CHAINS8(OP)
+#undef OP
+        } else if (kTest == 27) {   // dependent shared-memory load (pointer chase inside the lane's own word)
+            a0 = ((volatile uint32_t *)sm)[a0 & 31u]; a0 = ((volatile uint32_t *)sm)[a0 & 31u];
+            a0 = ((volatile uint32_t *)sm)[a0 & 31u]; a0 = ((volatile uint32_t *)sm)[a0 & 31u];
+            a0 = ((volatile uint32_t *)sm)[a0 & 31u]; a0 = ((volatile uint32_t *)sm)[a0 & 31u];
+            a0 = ((volatile uint32_t *)sm)[a0 & 31u]; a0 = ((volatile uint32_t *)sm)[a0 & 31u];
+        } else if (kTest == 28) {   // dependent SHFL
+#define OP(x) a0 = __shfl_sync(0xFFFFFFFFu, a0, (a0 + 1u) & 15u);
+            CHAINS8(OP)
+#undef OP
+        } else if (kTest == 29) {   // dependent funnel shift with a data-dependent amount
+#define OP(x) asm volatile("shf.l.wrap.b32 %0, %0, %1, %0;" : "+r"(a0) : "r"(b));
+            CHAINS8(OP) CHAINS8(OP)
+#undef OP
+        } else if (kTest == 30) {   // predicate produced by LOP3 (and + setp.ne fused) -> SEL
+#define OP(x) asm volatile("{.reg .pred p; .reg .u32 t; and.b32 t, %0, 0x8000; setp.ne.u32 p, t, 0; selp.u32 %0, %2, %1, p; xor.b32 %0, %0, %1;}" : "+r"(a0) : "r"(b), "r"(c));
+            CHAINS8(OP)
+#undef OP
         } else if (kTest == 15) {   // add that ptxas may turn into IMAD.IADD / IADD3
 #define OP(x) asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(b));
             CHAINS8(OP) CHAINS8(OP)
@@ -138,5 +186,17 @@ int main()
     run<15>("add rr x8 chains", 16, d_out, d_cyc);
     run<12>("ISETP+SEL x8 chains", 16, d_out, d_cyc);
     run<8>("FFMA rrr x8 chains", 16, d_out, d_cyc);
+    printf("--- dependent chains: cycles per ELEMENT of the chain (loop overhead ~10 cycles per 8 elements included)\n");
+    run<20>("ISETP -> SEL -> LOP3", 8, d_out, d_cyc);
+    run<30>("LOP3.P -> SEL -> LOP3", 8, d_out, d_cyc);
+    run<21>("SHF -> LOP3 -> LOP3", 8, d_out, d_cyc);
+    run<22>("IMAD -> ISETP -> SEL -> @SEL", 8, d_out, d_cyc);
+    run<23>("IMAD -> SHF -> LOP3 -> LOP3", 8, d_out, d_cyc);
+    run<24>("I2F -> FMUL -> F2I", 8, d_out, d_cyc);
+    run<25>("IMAD.HI dependent", 16, d_out, d_cyc);
+    run<26>("FADD dependent", 16, d_out, d_cyc);
+    run<27>("LDS dependent", 8, d_out, d_cyc);
+    run<28>("SHFL dependent", 8, d_out, d_cyc);
+    run<29>("SHF dependent", 16, d_out, d_cyc);
     return 0;
 }
