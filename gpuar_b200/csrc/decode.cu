@@ -44,32 +44,19 @@ __device__ __forceinline__ const uint32_t *clamp_ptr(const uint32_t *p, const ui
 constexpr uint32_t kRing = 8;        // per-lane ring of stream words in shared memory
 constexpr uint32_t kAhead = 3;       // words requested ahead of the reader
 
-#ifndef GPUAR_DEC_SPEC2
-#define GPUAR_DEC_SPEC2 7           // tuning knob: speculative node loads of the latency variant (decode_math.h)
-#endif
-
-// kernel variants: 0 throughput (decode_step), 1 latency (decode_step_latency), 2 latency without the quotient (decode_step_mul)
-template <int kVar>
+// kernel variants (template parameter kLatency): throughput (decode_step) and latency (decode_step_latency)
+template <bool kLatency>
 struct DecShared;
 template <>
-struct DecShared<0> {                        // throughput variant: 21504 B keeps 10 CTAs per SM
+struct DecShared<false> {                    // throughput variant: 21504 B keeps 10 CTAs per SM
     uint64_t tree[kTreeStored][32];          // lane l owns column l (banks 2l, 2l+1); root in registers
 };
 template <>
-struct DecShared<1> {                        // latency variant (at most 4 CTAs per SM: size does not matter)
+struct DecShared<true> {                     // latency variant (at most 4 CTAs per SM: size does not matter)
     Quad l1[4][32];                          // level-1 thresholds as 32-bit words (16 B per lane and node)
-    uint64_t l2[16][32];
-    uint64_t l3[64][32];
+    uint64_t l2[16][32];                     // packed (0, t0, t1, t2)
+    uint64_t l3[64][32];                     // leaves: packed inclusive sums
     uint32_t ring[kRing][32];                // 1024 B stream ring
-};
-template <>
-struct DecShared<3> : DecShared<1> {};
-template <>
-struct DecShared<2> {                        // every node as words: 43 KB
-    Quad l1[4][32];
-    Quad l2[16][32];
-    Quad l3[64][32];
-    uint32_t ring[kRing][32];
 };
 
 // 4-byte asynchronous global->shared copy (LDGSTS): no register, no scoreboard -- the stream
@@ -89,14 +76,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //          scheduler to itself (up to 4 warps per SM = 148 MiB: latency is everything);
 //   false  one word prefetched in a register, fed under a (divergent) branch -- fewer
 //          instructions per step; used when many warps per scheduler hide the latency.
-template <int kVar>
+template <bool kRingFeed>
 __global__ void __launch_bounds__(32)
 decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64_t *__restrict__ offsets,
               uint32_t stride, uint32_t n_packets, uint8_t *__restrict__ out, uint32_t packet,
               const uint64_t *__restrict__ count)
 {
-    constexpr bool kRingFeed = kVar != 0;
-    __shared__ __align__(16) DecShared<kVar> sm;
+    __shared__ __align__(16) DecShared<kRingFeed> sm;
     const uint32_t lane = lane_id();
     const uint32_t my = blockIdx.x * 32u + lane;
     if (count) {                                    // sharded decode: the chain discovery left the count on the device
@@ -110,13 +96,9 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     TopLevels top;                               // latency variants: the root's thresholds, level-1 copy
     uint64_t *tree = nullptr;
     LatTree lat{nullptr, nullptr, nullptr, 32u};
-    MulTree mul{nullptr, nullptr, nullptr, 32u};
-    if constexpr (kVar == 1 || kVar == 3) {
+    if constexpr (kRingFeed) {
         lat = LatTree{&sm.l1[0][lane], &sm.l2[0][lane], &sm.l3[0][lane], 32u};
         lat_tree_init(top, lat);
-    } else if constexpr (kVar == 2) {
-        mul = MulTree{&sm.l1[0][lane], &sm.l2[0][lane], &sm.l3[0][lane], 32u};
-        mul_tree_init(top, mul);
     } else {
         tree = &sm.tree[0][lane];
         dec_tree_init(root, tree, 32u);
@@ -196,12 +178,10 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     // one symbol of this lane's packet; `slot` = position of the byte inside the 32-bit store word
     auto step = [&](uint32_t i, uint32_t m, uint32_t sh, uint32_t slot) {
         const uint32_t T = 256u + i;
-        // latency variant: top levels decided by multiplication with speculative node loads; throughput variant: the
-        // quotient first, then the plain tree (the other way round was measured on both, profiles/r2_kernel_experiments.md)
+        // latency variant: every level decided by multiplication, speculative node loads; throughput variant: the
+        // quotient first, then the plain tree (the other way round was measured on both, profiles/r2_decode_v2.md)
         uint32_t s;
-        if constexpr (kVar == 1) s = decode_step_latency<GPUAR_DEC_SPEC2>(st, top, lat, T, m, sh, in);
-        else if constexpr (kVar == 2) s = decode_step_mul(st, top, mul, T, m, sh, in);
-        else if constexpr (kVar == 3) s = decode_step_mulp(st, top, lat, T, m, sh, in);
+        if constexpr (kRingFeed) s = decode_step_latency(st, top, lat, T, m, sh, in);
         else s = decode_step(st, root, tree, 32u, T, m, sh, in);
         packed = mad32(s, 1u << (8u * slot), packed);               // fields cannot overlap: a multiply-add, not shift + or
         // A step takes at most 16 bits and the window holds at least 33 after a refill: one refill (at most one
@@ -218,7 +198,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
         sh = shift_for(256u + i0);                                 // the shift is uniform over the round
         if (i0 + 32u <= min_raw) {
             // every lane of the warp has all 32 positions: no per-lane predicates
-            constexpr int kUnroll = kVar ? kDecUnrollLat : kDecUnroll;
+            constexpr int kUnroll = kRingFeed ? kDecUnrollLat : kDecUnroll;
 #pragma unroll kUnroll
             for (uint32_t j = 0; j < 32u; ++j) {
                 step(i0 + j, __shfl_sync(kFull, m_l, j), sh, j & 3u);
@@ -277,10 +257,10 @@ cudaError_t launch_selfcheck(uint64_t *d_mismatches, cudaStream_t st)
     return cudaGetLastError();
 }
 
-static int g_decode_path = 0;        // 0 auto, 1 latency variant, 2 throughput variant, 3 latency variant without the quotient
+static int g_decode_path = 0;        // 0 auto, 1 latency variant, 2 throughput variant
 bool set_decode_path(int path)
 {
-    if (path < 0 || path > 4) return false;
+    if (path < 0 || path > 2) return false;
     g_decode_path = path;
     return true;
 }
@@ -293,23 +273,19 @@ cudaError_t launch_decode(const uint8_t *d_payload, size_t readable, const uint6
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t grid = (packets + 31u) / 32u;
-    // The latency-optimised variant pays for its short chain with more instructions per step.  It wins while
-    // every warp has a scheduler to itself (4 per SM) and loses as soon as two warps share one
-    // (profiles/r1_s2_dec_switch.txt, profiles/r2_decode_v2.md).  GPUAR_OPT_DECODE_PATH forces one of them
+    // The latency-optimised variant pays for its short chain with more instructions per step and more shared-memory
+    // traffic.  Measured (profiles/r2_decode_v2.md): it wins up to two warps per scheduler (8 CTAs per SM: 296 MiB
+    // 2.18 against 2.33 ms; 148 MiB 1.28 against 2.05 ms) and loses from 10 CTAs per SM on, which no longer fit in one
+    // wave of its 23.5 KB of shared memory (370 MiB: 3.35 against 2.82 ms).  GPUAR_OPT_DECODE_PATH forces one of them
     // (tests run both on the same streams); GPUAR_B200_DEC_RING_MAX=<CTAs> moves the switch (tuning aid).
     static const long forced = [] { const char *e = getenv("GPUAR_B200_DEC_RING_MAX"); return e && *e ? atol(e) : -1L; }();
-    uint32_t ring_max = forced >= 0 ? (uint32_t)forced : (uint32_t)sms * 4u;
-    if (g_decode_path == 1 || g_decode_path >= 3) ring_max = 0xFFFFFFFFu;
+    uint32_t ring_max = forced >= 0 ? (uint32_t)forced : (uint32_t)sms * 8u;
+    if (g_decode_path == 1) ring_max = 0xFFFFFFFFu;
     if (g_decode_path == 2) ring_max = 0u;
-    // latency regime: the variant that decides every level by multiplication, packed lower levels (kVar 3)
-    if (g_decode_path == 3)
-        decode_kernel<2><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet, d_count);
-    else if (g_decode_path == 1)
-        decode_kernel<1><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet, d_count);
-    else if (grid <= ring_max)
-        decode_kernel<3><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet, d_count);
+    if (grid <= ring_max)
+        decode_kernel<true><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet, d_count);
     else
-        decode_kernel<0><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet, d_count);
+        decode_kernel<false><<<grid, 32, 0, st>>>(d_payload, readable, d_offsets, stride, packets, d_out, packet, d_count);
     count_launch();
     return cudaGetLastError();
 }

@@ -4,18 +4,20 @@
 // Same arithmetic as the reference (getUnscaledCode src/gpuar_kernel.cu:703-716,
 // getSymbolFromProbability :727-763, applySymbolRange :256-288, readEncodedBits :787-836); what
 // changed against the first-generation step (coder_math.h: tree_decode / tree_decode_spec_range +
-// narrow_total + advance_code_total) is the bookkeeping around it -- the instruction count is what
-// bounds the decoder (profiles/r2_kernel_experiments.md):
+// narrow_total + advance_code_total) is the bookkeeping around it -- the instruction count and, for
+// a lone warp, the length of the dependent chain are what bound the decoder (profiles/r2_decode_v2.md):
 //   * the decoder carries D = code - lower bound (mod 2^16) instead of `code`: the numerator of the
 //     quotient is D * T + T - 1 directly, and an underflow step flips bit 15 of the code AND drops
 //     bit 15 of the shifted lower bound, so D' = ((D - qb) << t | next t bits) mod 2^16 needs
 //     neither the flip nor the subtraction;
 //   * the leaves hold INCLUSIVE prefix sums (s0, s1, s2, s3) of their four symbol counts -- s3 is
-//     the leaf's own total -- so cum[s] and cum[s+1] both come out of the leaf with one byte
-//     permute and no level has to hand "what is left above the target" down to the next one;
-//   * the latency variant keeps the root as three registers and the four level-1 nodes as three
-//     32-bit words each (no field extraction on the chain, updates are one add per threshold),
-//     and its speculative four-way selects are written on predicates (two SEL per word).
+//     the leaf's own total -- so cum[s] and cum[s+1] both come out of the leaf and no level has to
+//     hand "what is left above the target" down to the next one;
+//   * throughput variant (decode_step): quotient with a one-sided correction, then four packed levels;
+//   * latency variant (decode_step_latency): no quotient at all -- every level is decided by the sign
+//     of num - threshold * range, the next level's four candidate nodes are loaded before the child
+//     is known and picked with selects on predicates, and the interval narrowing takes the PRODUCTS
+//     cum * range straight from the sign tests.
 #pragma once
 #include "coder_math.h"
 
@@ -178,10 +180,15 @@ GPUAR_HD uint32_t decode_step(DecState &st, uint64_t &root, uint64_t *nodes, uin
 }
 
 // ---------------------------------------------------------------- latency variant
-// target = floor(num / range), so for an integer threshold t:  t <= target  <=>  t * range <= num.  The two top
-// levels are decided by the sign of num - t * range while the divide is in flight, and no node load waits for
-// its child index: the four candidates of a level are requested as soon as their parent is known and the right
-// one is picked with predicated selects.  (t * range <= 8448 * 65536 < 2^30, num < 2^30: signs are exact.)
+// target = floor(num / range), so for an integer threshold t:  t <= target  <=>  t * range <= num.  Every level is
+// decided by the sign of num - t * range (t * range <= 16368 * 65536 < 2^30, num < 2^30: signs are exact), so there
+// is no divide, no conversion and no byte permute on the chain, and no node load waits for its child index: the four
+// candidates of a level are requested as soon as their parent is known and the right one is picked with two
+// predicated selects per word.  Neither cum[s] nor cum[s+1] is ever formed: the interval narrowing needs the
+// PRODUCTS cum * range, and num - cum * range is exactly what the sign test of the chosen threshold computed.
+// The root is three registers and the four level-1 nodes are three 32-bit words each (nothing to extract, one add
+// per threshold to update); level 2 and the leaves stay packed (8 bytes: a third of the shared-memory traffic of
+// unpacked nodes, which was measured too -- faster only with a single warp per SM).
 struct LatTree {
     Quad *l1;            // [4][lanes]   thresholds of the level-1 nodes
     uint64_t *l2;        // [16][lanes]  packed
@@ -214,105 +221,6 @@ GPUAR_HD uint32_t pick4p(bool p0, bool p1, bool p2, uint32_t a, uint32_t b, uint
 }
 GPUAR_HD uint32_t neg_bit(uint32_t d) { return d >> 31; }
 
-template <int kSpec = 7>      // bit 1 / bit 2: speculative loads of the level-2 candidates / of the leaf candidates
-GPUAR_HD uint32_t decode_step_latency(DecState &st, TopLevels &top, const LatTree &tr, uint32_t T,
-                                      uint32_t m, uint32_t sh, BitSource &in)
-{
-    const uint32_t lanes = tr.lanes;
-    uint32_t &T0 = top.T0, &T1 = top.T1, &T2 = top.T2;
-    const uint32_t num = st.D * T + (T - 1u);
-    const uint32_t nr = 0u - st.R;
-    // level-1 candidates: loaded during the previous step
-    const Quad qa1 = top.c[0], qb1 = top.c[1], qc1 = top.c[2], qd1 = top.c[3];
-    // level 0
-    const uint32_t e0 = T0 * nr + num, e1 = T1 * nr + num, e2 = T2 * nr + num;      // num - threshold * range
-    const bool p0 = (int32_t)e0 < 0, p1 = (int32_t)e1 < 0, p2 = (int32_t)e2 < 0;
-    const uint32_t c0 = 3u - (neg_bit(e0) + neg_bit(e1) + neg_bit(e2));
-    uint64_t *const g2 = tr.l2 + c0 * 4u * lanes;
-    uint64_t a2 = 0, b2 = 0, c2n = 0, d2 = 0;
-    if (kSpec & 2) a2 = g2[0], b2 = g2[lanes], c2n = g2[2u * lanes], d2 = g2[3u * lanes];
-    Quad n1;
-    n1.x = pick4p(p0, p1, p2, qa1.x, qb1.x, qc1.x, qd1.x);
-    n1.y = pick4p(p0, p1, p2, qa1.y, qb1.y, qc1.y, qd1.y);
-    n1.z = pick4p(p0, p1, p2, qa1.z, qb1.z, qc1.z, qd1.z);
-    n1.w = 0u;
-    const uint32_t num1 = pick4p(p0, p1, p2, num, e0, e1, e2);    // what is left of num below the child
-    const uint32_t below0 = pick4p(p0, p1, p2, 0u, T0, T1, T2);
-    T0 += neg_bit(e0), T1 += neg_bit(e1), T2 += neg_bit(e2);      // +1 on every threshold above the target
-    // level 1
-    const uint32_t f0 = n1.x * nr + num1, f1 = n1.y * nr + num1, f2 = n1.z * nr + num1;
-    const bool k0 = (int32_t)f0 < 0, k1 = (int32_t)f1 < 0, k2 = (int32_t)f2 < 0;
-    const uint32_t c1 = 3u - (neg_bit(f0) + neg_bit(f1) + neg_bit(f2));
-    uint32_t idx = c0 * 4u + c1;
-    uint64_t *const p2n = g2 + c1 * lanes;
-    uint64_t *const g3 = tr.l3 + idx * 4u * lanes;
-    uint64_t a3 = 0, b3 = 0, c3n = 0, d3 = 0;
-    if (kSpec & 4) a3 = g3[0], b3 = g3[lanes], c3n = g3[2u * lanes], d3 = g3[3u * lanes];
-    uint32_t lo2, hi2;
-    if (kSpec & 2) {
-        lo2 = pick4p(k0, k1, k2, (uint32_t)a2, (uint32_t)b2, (uint32_t)c2n, (uint32_t)d2);
-        hi2 = pick4p(k0, k1, k2, (uint32_t)(a2 >> 32), (uint32_t)(b2 >> 32), (uint32_t)(c2n >> 32), (uint32_t)(d2 >> 32));
-    } else {
-        const uint64_t v = *p2n;
-        lo2 = (uint32_t)v, hi2 = (uint32_t)(v >> 32);
-    }
-    const uint32_t below1 = below0 + pick4p(k0, k1, k2, 0u, n1.x, n1.y, n1.z);
-    n1.x += neg_bit(f0), n1.y += neg_bit(f1), n1.z += neg_bit(f2);
-    tr.l1[c0 * lanes] = n1;
-    top.c[0] = tr.l1[0], top.c[1] = tr.l1[lanes], top.c[2] = tr.l1[2u * lanes], top.c[3] = tr.l1[3u * lanes];
-    // levels 2 and 3 on the quotient
-    const uint32_t target = divide_floor(num, st.R);
-    uint32_t rem = target - below1;
-    uint32_t lo3, hi3;
-    uint32_t c2;
-    if (kSpec & 4) {
-        // the comparison bits of level 2 once more as predicates, for the pick among the four leaves
-        const uint32_t rr = rem * 0x10001u + 0x80008000u;
-        const uint32_t dlo = rr - lo2, dhi = rr - hi2;
-        const bool j0 = (int32_t)dlo >= 0, j1 = (dhi & 0x8000u) == 0u, j2 = (int32_t)dhi >= 0;   // threshold above rem
-        lo3 = pick4p(j0, j1, j2, (uint32_t)a3, (uint32_t)b3, (uint32_t)c3n, (uint32_t)d3);
-        hi3 = pick4p(j0, j1, j2, (uint32_t)(a3 >> 32), (uint32_t)(b3 >> 32), (uint32_t)(c3n >> 32), (uint32_t)(d3 >> 32));
-        c2 = packed_level(lo2, hi2, rem);
-    } else {
-        c2 = packed_level(lo2, hi2, rem);
-        const uint64_t v = g3[c2 * lanes];
-        lo3 = (uint32_t)v, hi3 = (uint32_t)(v >> 32);
-    }
-    *p2n = ((uint64_t)hi2 << 32) | lo2;
-    idx = idx * 4u + c2;
-    uint32_t below, upto;
-    const uint32_t c3 = leaf_level(lo3, hi3, rem, below, upto);
-    g3[c2 * lanes] = ((uint64_t)hi3 << 32) | lo3;
-    const uint32_t base = target - rem;
-    narrow_track(st, base + below, base + upto, m, sh, in);
-    return idx * 4u + c3;
-}
-
-// ---------------------------------------------------------------- latency variant, no quotient at all
-// All four levels are decided by the sign of num - threshold * range, every node is three (the leaves: four)
-// 32-bit words -- nothing to extract -- and neither cum[s] nor cum[s+1] is ever formed: what the interval
-// narrowing needs are the PRODUCTS cum * range, and num - cum * range is exactly the value the sign test of the
-// chosen threshold computed.  Per level: three multiply-adds, three compares, two selects per word; the chain
-// of a step is four of those, then the narrowing.  No divide, no conversion, no byte permute.
-// 16 bytes per node and lane: 42 KB per warp, which only the regime of this variant can afford (at most one
-// warp per scheduler), and four shared-memory wavefronts per load -- with more than two warps on an SM the
-// packed variant above moves less data.
-struct MulTree {
-    Quad *l1;            // [4][lanes]   thresholds x, y, z
-    Quad *l2;            // [16][lanes]
-    Quad *l3;            // [64][lanes]  leaves: inclusive prefix sums x, y, z, w
-    uint32_t lanes;
-};
-
-GPUAR_HD void mul_tree_init(TopLevels &top, const MulTree &tr)
-{
-    top.T0 = 64, top.T1 = 128, top.T2 = 192;
-    for (uint32_t q = 0; q < 4; ++q) top.c[q] = Quad{16u, 32u, 48u, 0u};
-    for (uint32_t q = 0; q < 4; ++q) tr.l1[q * tr.lanes] = Quad{16u, 32u, 48u, 0u};
-    for (uint32_t q = 0; q < 16; ++q) tr.l2[q * tr.lanes] = Quad{4u, 8u, 12u, 0u};
-    for (uint32_t q = 0; q < 64; ++q) tr.l3[q * tr.lanes] = Quad{1u, 2u, 3u, 4u};
-}
-
 GPUAR_HD void narrow_track_products(DecState &st, uint32_t lo_r, uint32_t hi_r, uint32_t m, uint32_t sh, BitSource &in)
 {
     const uint32_t qa = div_total(hi_r, m, sh);
@@ -328,72 +236,7 @@ GPUAR_HD void narrow_track_products(DecState &st, uint32_t lo_r, uint32_t hi_r, 
     in.skip(t);
 }
 
-GPUAR_HD uint32_t decode_step_mul(DecState &st, TopLevels &top, const MulTree &tr, uint32_t T,
-                                  uint32_t m, uint32_t sh, BitSource &in)
-{
-    const uint32_t lanes = tr.lanes;
-    uint32_t &T0 = top.T0, &T1 = top.T1, &T2 = top.T2;
-    const uint32_t num = st.D * T + (T - 1u);
-    const uint32_t nr = 0u - st.R;
-    const Quad qa1 = top.c[0], qb1 = top.c[1], qc1 = top.c[2], qd1 = top.c[3];
-    // level 0
-    const uint32_t e0 = T0 * nr + num, e1 = T1 * nr + num, e2 = T2 * nr + num;      // num - threshold * range
-    const bool p0 = (int32_t)e0 < 0, p1 = (int32_t)e1 < 0, p2 = (int32_t)e2 < 0;
-    const uint32_t c0 = 3u - (neg_bit(e0) + neg_bit(e1) + neg_bit(e2));
-    Quad *const g2 = tr.l2 + c0 * 4u * lanes;
-    const Quad qa2 = g2[0], qb2 = g2[lanes], qc2 = g2[2u * lanes], qd2 = g2[3u * lanes];
-    Quad n1;
-    n1.x = pick4p(p0, p1, p2, qa1.x, qb1.x, qc1.x, qd1.x);
-    n1.y = pick4p(p0, p1, p2, qa1.y, qb1.y, qc1.y, qd1.y);
-    n1.z = pick4p(p0, p1, p2, qa1.z, qb1.z, qc1.z, qd1.z);
-    n1.w = 0u;
-    const uint32_t num1 = pick4p(p0, p1, p2, num, e0, e1, e2);    // what is left of num below the child
-    T0 += neg_bit(e0), T1 += neg_bit(e1), T2 += neg_bit(e2);      // +1 on every threshold above the target
-    // level 1
-    const uint32_t f0 = n1.x * nr + num1, f1 = n1.y * nr + num1, f2 = n1.z * nr + num1;
-    const bool k0 = (int32_t)f0 < 0, k1 = (int32_t)f1 < 0, k2 = (int32_t)f2 < 0;
-    const uint32_t c1 = 3u - (neg_bit(f0) + neg_bit(f1) + neg_bit(f2));
-    uint32_t idx = c0 * 4u + c1;
-    Quad *const g3 = tr.l3 + idx * 4u * lanes;
-    const Quad qa3 = g3[0], qb3 = g3[lanes], qc3 = g3[2u * lanes], qd3 = g3[3u * lanes];
-    Quad n2;
-    n2.x = pick4p(k0, k1, k2, qa2.x, qb2.x, qc2.x, qd2.x);
-    n2.y = pick4p(k0, k1, k2, qa2.y, qb2.y, qc2.y, qd2.y);
-    n2.z = pick4p(k0, k1, k2, qa2.z, qb2.z, qc2.z, qd2.z);
-    n2.w = 0u;
-    const uint32_t num2 = pick4p(k0, k1, k2, num1, f0, f1, f2);
-    n1.x += neg_bit(f0), n1.y += neg_bit(f1), n1.z += neg_bit(f2);
-    tr.l1[c0 * lanes] = n1;
-    top.c[0] = tr.l1[0], top.c[1] = tr.l1[lanes], top.c[2] = tr.l1[2u * lanes], top.c[3] = tr.l1[3u * lanes];
-    // level 2
-    const uint32_t g0 = n2.x * nr + num2, g1 = n2.y * nr + num2, g2v = n2.z * nr + num2;
-    const bool j0 = (int32_t)g0 < 0, j1 = (int32_t)g1 < 0, j2 = (int32_t)g2v < 0;
-    const uint32_t c2 = 3u - (neg_bit(g0) + neg_bit(g1) + neg_bit(g2v));
-    Quad n3;
-    n3.x = pick4p(j0, j1, j2, qa3.x, qb3.x, qc3.x, qd3.x);
-    n3.y = pick4p(j0, j1, j2, qa3.y, qb3.y, qc3.y, qd3.y);
-    n3.z = pick4p(j0, j1, j2, qa3.z, qb3.z, qc3.z, qd3.z);
-    n3.w = pick4p(j0, j1, j2, qa3.w, qb3.w, qc3.w, qd3.w);
-    const uint32_t num3 = pick4p(j0, j1, j2, num2, g0, g1, g2v);
-    n2.x += neg_bit(g0), n2.y += neg_bit(g1), n2.z += neg_bit(g2v);
-    g2[c1 * lanes] = n2;
-    idx = idx * 4u + c2;
-    // the leaf
-    const uint32_t h0 = n3.x * nr + num3, h1 = n3.y * nr + num3, h2 = n3.z * nr + num3, h3 = n3.w * nr + num3;
-    const bool r0 = (int32_t)h0 < 0, r1 = (int32_t)h1 < 0, r2 = (int32_t)h2 < 0;
-    const uint32_t c3 = 3u - (neg_bit(h0) + neg_bit(h1) + neg_bit(h2));
-    const uint32_t num_lo = pick4p(r0, r1, r2, num3, h0, h1, h2);     // num - cum[s] * range
-    const uint32_t num_hi = pick4p(r0, r1, r2, h0, h1, h2, h3);       // num - cum[s+1] * range
-    n3.x += neg_bit(h0), n3.y += neg_bit(h1), n3.z += neg_bit(h2), n3.w += 1u;
-    g3[c2 * lanes] = n3;
-    narrow_track_products(st, num - num_lo, num - num_hi, m, sh, in);
-    return idx * 4u + c3;
-}
-
-// ---------------------------------------------------------------- latency variant, no quotient, packed lower levels
-// decode_step_mul with the level-2 nodes and the leaves in the packed 8-byte form of the other variants (a third
-// of the shared-memory traffic): the thresholds are extracted with one shift or mask each before the multiply-adds.
-GPUAR_HD uint32_t decode_step_mulp(DecState &st, TopLevels &top, const LatTree &tr, uint32_t T, uint32_t m, uint32_t sh,
+GPUAR_HD uint32_t decode_step_latency(DecState &st, TopLevels &top, const LatTree &tr, uint32_t T, uint32_t m, uint32_t sh,
                                    BitSource &in)
 {
     const uint32_t lanes = tr.lanes;

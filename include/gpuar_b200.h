@@ -286,8 +286,7 @@ void garDecompressExecutor(const uint8_t *source, size_t size, uint8_t *destinat
                                         or a power of two 4..128 (32 KiB .. 1 MiB of input per CTA) */
 #define GPUAR_OPT_DECODE_PATH 4      /* decode kernel: 0 auto (default: by packet count), 1 latency variant
                                         (speculative node loads, for inputs that leave warp schedulers idle),
-                                        2 throughput variant, 3 latency variant that decides every tree level
-                                        by multiplication (no quotient) */
+                                        2 throughput variant */
 int gpuar_b200_set_option(int key, long long value);
 
 /* ----------------------------------------------------------- measurement hooks

@@ -173,17 +173,15 @@ uint32_t host_model_decode_packet_total(const uint8_t *payload, size_t readable,
 }
 
 // the second-generation decoder step (decode_math.h) exactly as a lane of decode_kernel runs it:
-// variant 0 = throughput (decode_step), 1..4 = latency (decode_step_latency<7 / 5 / 3 / 1>), 5 = decode_step_mul, 6 = decode_step_mulp
+// variant 0 = throughput (decode_step), 1 = latency (decode_step_latency)
 uint32_t host_model_decode_packet_v2(const uint8_t *payload, size_t readable, size_t off, uint8_t *out, int variant)
 {
     std::vector<uint64_t> tree(kTreeStored);
-    std::vector<Quad> l1(4), q2(16), q3(64);
-    MulTree mt{l1.data(), q2.data(), q3.data(), 1u};
+    std::vector<Quad> l1(4);
     uint64_t root = 0;
     TopLevels top;
     LatTree tr{l1.data(), tree.data() + 4, tree.data() + 20, 1u};
     if (variant == 0) dec_tree_init(root, tree.data(), 1);
-    else if (variant == 5) mul_tree_init(top, mt);
     else lat_tree_init(top, tr);
     const uint32_t *const words = reinterpret_cast<const uint32_t *>(payload);
     const uint32_t *const wend = words + (readable >> 2) - 1;
@@ -208,18 +206,11 @@ uint32_t host_model_decode_packet_v2(const uint8_t *payload, size_t readable, si
         const uint32_t T = 256u + i;
         uint32_t sh;
         const uint32_t m = magic_for(T, sh);
-        uint32_t s;
-        switch (variant) {
-        case 0: s = decode_step(st, root, tree.data(), 1, T, m, sh, in); break;
-        case 1: s = decode_step_latency<7>(st, top, tr, T, m, sh, in); break;
-        case 2: s = decode_step_latency<5>(st, top, tr, T, m, sh, in); break;
-        case 3: s = decode_step_latency<3>(st, top, tr, T, m, sh, in); break;
-        case 5: s = decode_step_mul(st, top, mt, T, m, sh, in); break;
-        case 6: s = decode_step_mulp(st, top, tr, T, m, sh, in); break;
-        default: s = decode_step_latency<1>(st, top, tr, T, m, sh, in); break;
-        }
+        const uint32_t s = variant == 0 ? decode_step(st, root, tree.data(), 1, T, m, sh, in)
+                                        : decode_step_latency(st, top, tr, T, m, sh, in);
         out[i] = (uint8_t)s;
-        if (in.hungry()) { in.feed(ahead); ++wp; ahead = word(wp); }
+        // the kernels refill every second step (a step takes at most 16 bits, a refill restores 33)
+        if ((i & 1u) && in.hungry()) { in.feed(ahead); ++wp; ahead = word(wp); }
     }
     return raw;
 }

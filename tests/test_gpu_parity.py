@@ -199,7 +199,7 @@ def test_decode_ragged_sizes(dev, n):
     assert np.array_equal(got, data)
 
 
-@pytest.mark.parametrize("path", ["latency", "throughput", "latency_mul", "latency_mulp"])
+@pytest.mark.parametrize("path", ["latency", "throughput"])
 def test_both_decode_kernels_are_bit_exact(dev, path):
     # the two decode kernels (decode_math.h: decode_step_latency / decode_step) on the same streams: golden
     # vectors made by the reference, ragged tails, a long-underflow stream, one-symbol packets
@@ -208,7 +208,7 @@ def test_both_decode_kernels_are_bit_exact(dev, path):
     cases = [make_input(VECTORS[name]) for name in SMALL]
     cases += [D.mixed(5, 8192 * 70 + 123), D.zeros(8192 * 3 + 1), D.uniform(9, 8192 * 40 - 1),
               rng.choice(np.array([127, 128], np.uint8), size=8192 * 33)]
-    _lib.set_option(_lib.OPT_DECODE_PATH, {"latency": 1, "throughput": 2, "latency_mul": 3, "latency_mulp": 4}[path])
+    _lib.set_option(_lib.OPT_DECODE_PATH, {"latency": 1, "throughput": 2}[path])
     try:
         for data in cases:
             got = dev.decode_bytes(to_dev(O.encode(data))).cpu().numpy()

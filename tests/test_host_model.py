@@ -54,7 +54,7 @@ def model_encode(lib, data, packet=8192, ws=False):
 
 def model_decode(lib, pay, n, early=False, total=False, v2=None):
     fn = lib.host_model_decode_packet_early if early else lib.host_model_decode_packet
-    if v2 is not None:                     # decode_math.h: 0 = throughput step, 1..4 = latency step, 5 = no-quotient step
+    if v2 is not None:                     # decode_math.h: 0 = throughput step, 1 = latency step
         def fn(p, r, o, out):
             return lib.host_model_decode_packet_v2(p, r, o, out, v2)
     if total:
@@ -99,7 +99,7 @@ def test_kernel_math_matches_reference_golden(model, name):
     assert np.array_equal(model_decode(model, pay, data.size, early=True), data)
     assert np.array_equal(model_decode(model, pay, data.size, early=True, total=True), data)
     assert np.array_equal(model_decode(model, pay, data.size, total=True), data)
-    for v in range(7):
+    for v in range(2):
         assert np.array_equal(model_decode(model, pay, data.size, v2=v), data)
 
 
@@ -113,7 +113,7 @@ def test_kernel_math_ragged_lengths(model, n):
         assert np.array_equal(model_decode(model, pay, n, early=True), data)
         assert np.array_equal(model_decode(model, pay, n, early=True, total=True), data)
         assert np.array_equal(model_decode(model, pay, n, total=True), data)
-        for v in range(7):
+        for v in range(2):
             assert np.array_equal(model_decode(model, pay, n, v2=v), data)
 
 
@@ -129,7 +129,7 @@ def test_kernel_math_other_packet_sizes(model, packet):
     assert np.array_equal(model_decode(model, pay, data.size, early=True), data)
     assert np.array_equal(model_decode(model, pay, data.size, early=True, total=True), data)
     assert np.array_equal(model_decode(model, pay, data.size, total=True), data)
-    for v in range(7):
+    for v in range(2):
         assert np.array_equal(model_decode(model, pay, data.size, v2=v), data)
 
 
@@ -143,5 +143,5 @@ def test_kernel_math_long_underflow_runs(model):
         assert np.array_equal(model_encode(model, data, ws=True), pay)
         assert np.array_equal(model_decode(model, pay, 8192), data)
         assert np.array_equal(model_decode(model, pay, 8192, early=True, total=True), data)
-        for v in range(7):
+        for v in range(2):
             assert np.array_equal(model_decode(model, pay, 8192, v2=v), data)

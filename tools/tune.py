@@ -40,7 +40,7 @@ def main():
     ap.add_argument("--gen", default="uniform", choices=["uniform", "and3", "mixed"])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--decode", action="store_true")
-    ap.add_argument("--dec-paths", default="0", help="GPUAR_OPT_DECODE_PATH values to time (0 auto, 1 latency, 2 throughput, 3 latency without the quotient)")
+    ap.add_argument("--dec-paths", default="0", help="GPUAR_OPT_DECODE_PATH values to time (0 auto, 1 latency, 2 throughput)")
     args = ap.parse_args()
     dev = codec.DeviceCodec(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
