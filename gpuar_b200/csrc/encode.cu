@@ -24,6 +24,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "encode_math.h"
 #include "kernels.h"
 #include "lookback.cuh"
 #include "shard.cuh"
@@ -54,14 +55,10 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
     const uint32_t max_len = __reduce_max_sync(kFull, len);
     const uint32_t min_len = __reduce_min_sync(kFull, mine ? len : packet);
 
-    uint32_t L = 0, V = 0, pend = 0;
+    EncState st{0u, 65536u};                                      // plain window of the lower bound, range (encode_math.h)
     uint8_t *const slot = slots + (size_t)my * slot_stride;
-    BitSink out;
-    out.acc = 0;
-    out.nb = 0;
-    out.widx = 0;
-    out.wcap = mine ? ((slot_stride - kHdr) >> 2) : 0u;
-    out.words = reinterpret_cast<uint32_t *>(slot + kHdr);
+    CarrySink out;
+    out.start(reinterpret_cast<uint32_t *>(slot + kHdr), mine ? ((slot_stride - kHdr) >> 2) : 0u);
 
     // 16 input bytes per lane per half round, fetched one half round ahead.  The read may
     // run up to 15 bytes past n inside the caller's 16-byte-rounded buffer (API contract).
@@ -73,29 +70,33 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
 
     // pipeline registers
     uint32_t lo_n = 0, cnt_n = 1;            // MODEL output for the next CODER step
-    uint32_t pk = 0, pu = 0, pU = 0;         // CODER output not yet turned into bits
+    uint32_t p_inc = 0, p_t = 0;             // CODER output not yet in the bit sink: the bits that left the window (+ carry), their count
     bool pending = false;
     if (len) tree_encode(root, tree, 32u, bufA.x & 0xFFu, lo_n, cnt_n);          // MODEL(0)
 
+    // BITS: append the step's bits; a carry that leaves the sink (through at least 16 pending one-bits: the
+    // reference's pend >= 16) is added to the words already stored, under one warp-uniform vote
+    auto bits = [&](auto fast_tag) {
+        constexpr bool kFast = decltype(fast_tag)::value;
+        const uint32_t stored = out.widx;
+        const bool carry = out.push(p_inc, p_t);
+        if (kFast ? __any_sync(kFull, carry) : carry) {
+            if (carry) out.carry_into_stored(stored);
+        }
+    };
+
     // iteration i: BITS(i-1), CODER(i), MODEL(i+1).  kFast: every lane has positions i and
-    // i+1 and a pending field, so nothing is predicated per lane.
+    // i+1 and a pending step, so nothing is predicated per lane.
     auto iter = [&](auto fast_tag, uint32_t i, uint32_t s_next, uint32_t m, uint32_t sh) {
         constexpr bool kFast = decltype(fast_tag)::value;
         if (kFast) {
-            if (__any_sync(kFull, emit_is_long(pend, pk))) {      // warp-uniform and almost never taken
-                if (emit_is_long(pend, pk)) {
-                    emit_long(out, pend, pk, pu, pU);
-                    pk = 0;                                       // the field below becomes a no-op
-                    pu = 0;
-                }
-            }
-            emit_field(out, pend, pk, pu, pU);
-            narrow_renorm(L, V, lo_n, lo_n + cnt_n, m, sh, pk, pu, pU);
+            bits(fast_tag);
+            narrow_plain(st, lo_n, lo_n + cnt_n, m, sh, p_inc, p_t);
             tree_encode(root, tree, 32u, s_next, lo_n, cnt_n);
         } else {
-            if (pending) emit_symbol(out, pend, pk, pu, pU);
+            if (pending) bits(fast_tag);
             pending = i < len;
-            if (pending) narrow_renorm(L, V, lo_n, lo_n + cnt_n, m, sh, pk, pu, pU);
+            if (pending) narrow_plain(st, lo_n, lo_n + cnt_n, m, sh, p_inc, p_t);
             if (i + 1u < len) tree_encode(root, tree, 32u, s_next, lo_n, cnt_n);
         }
     };
@@ -137,11 +138,11 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
         half(bufB, bufA.x, fast, i0, 1u, m_l, sh);
         bufB = fetch(2u * r + 3u);
     }
-    if (pending) emit_symbol(out, pend, pk, pu, pU);              // BITS of the last step
+    if (pending) bits(std::false_type{});                         // BITS of the last step
 
     uint32_t comp = 0;
     if (mine) {
-        comp = finish_packet(out, L, pend, slot, len);
+        comp = finish_packet_plain(out, st.Lp, slot, len);
         if (sizes) sizes[my] = comp;
     }
     if (tg.world > 1u) {                                          // sharded encode: this rank's total for the other ranks

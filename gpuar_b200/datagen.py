@@ -92,6 +92,41 @@ def adversarial_packet() -> np.ndarray:
     return out
 
 
+def straddle_packet(n: int = 8192, report: bool = False):
+    """n bytes built greedily so that the coder's interval keeps containing the midpoint of its window: every
+    step takes the symbol whose sub-interval straddles 0x8000 (when there is one), so the reference's
+    pending-underflow counter grows into the hundreds -- far beyond the 16 bits the encoders keep pending, which
+    is what their rare paths (long underflow runs / a carry into words already stored) need to be exercised.
+    Follows the reference coder step (src/gpuar_kernel.cu:256-288, 321-367) with plain integers."""
+    cnt = np.ones(256, dtype=np.int64)
+    lo, hi, pend, max_pend = 0, 0xFFFF, 0, 0
+    out = np.empty(n, dtype=np.uint8)
+    for i in range(n):
+        total = 256 + i
+        cum = np.concatenate(([0], np.cumsum(cnt)))
+        rng = hi - lo + 1
+        lows = lo + (cum[:-1] * rng) // total
+        highs = lo + (cum[1:] * rng) // total - 1
+        cand = np.nonzero((lows < 0x8000) & (highs >= 0x8000))[0]
+        s = int(cand[0]) if cand.size else int(np.argmax(highs >= 0x8000 if lo < 0x8000 else highs >= lows))
+        out[i] = s
+        lo, hi = int(lows[s]), int(highs[s])
+        cnt[s] += 1
+        while True:
+            if (lo ^ hi) & 0x8000 == 0:
+                pend = 0
+            elif (lo & 0x4000) and not (hi & 0x4000):
+                pend += 1
+                max_pend = max(max_pend, pend)
+                lo &= 0x3FFF
+                hi |= 0x4000
+            else:
+                break
+            lo = (lo << 1) & 0xFFFF
+            hi = ((hi << 1) | 1) & 0xFFFF
+    return (out, max_pend) if report else out
+
+
 GENERATORS = {"uniform": uniform, "and3": and3, "and2": and2, "mixed": mixed}
 
 

@@ -10,6 +10,7 @@
 
 #include "../gpuar_b200/csrc/coder_math.h"
 #include "../gpuar_b200/csrc/decode_math.h"
+#include "../gpuar_b200/csrc/encode_math.h"
 
 using namespace gpuar;
 
@@ -74,6 +75,35 @@ uint32_t host_model_encode_packet_ws(const uint8_t *x, uint32_t n, uint8_t *slot
     return finish_packet(out, L, pend, slot, n);
 }
 
+// how often host_model_encode_packet_plain had to carry into words it had already stored (the rare path of the
+// kernels): lets the tests assert that their long-underflow inputs really exercise it
+static uint64_t g_carry_events = 0;
+uint64_t host_model_carry_events(void) { return g_carry_events; }
+
+// the second-generation coder + bit output (encode_math.h): plain window, carry into the pending bits
+uint32_t host_model_encode_packet_plain(const uint8_t *x, uint32_t n, uint8_t *slot, uint32_t slot_bytes)
+{
+    std::vector<uint64_t> tree(kTreeStored);
+    uint64_t root;
+    enc_tree_init(root, tree.data(), 1);
+    EncState st{0u, 65536u};
+    CarrySink out;
+    out.start(reinterpret_cast<uint32_t *>(slot + kHdr), (slot_bytes - kHdr) >> 2);
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t sh;
+        const uint32_t m = magic_for(256u + i, sh);
+        uint32_t lo, cnt, inc, t;
+        tree_encode(root, tree.data(), 1, x[i], lo, cnt);
+        narrow_plain(st, lo, lo + cnt, m, sh, inc, t);
+        const uint32_t before = out.widx;
+        if (out.push(inc, t)) {
+            out.carry_into_stored(before);
+            ++g_carry_events;
+        }
+    }
+    return finish_packet_plain(out, st.Lp, slot, n);
+}
+
 static size_t encode_stream_with(uint32_t (*enc)(const uint8_t *, uint32_t, uint8_t *, uint32_t), const uint8_t *in,
                                  size_t n, uint8_t *payload, uint32_t packet)
 {
@@ -86,6 +116,11 @@ static size_t encode_stream_with(uint32_t (*enc)(const uint8_t *, uint32_t, uint
         pos += len;
     }
     return pos;
+}
+
+size_t host_model_encode_stream_plain(const uint8_t *in, size_t n, uint8_t *payload, uint32_t packet)
+{
+    return encode_stream_with(host_model_encode_packet_plain, in, n, payload, packet);
 }
 
 size_t host_model_encode_stream_ws(const uint8_t *in, size_t n, uint8_t *payload, uint32_t packet)

@@ -71,10 +71,31 @@ def test_encode_packet_sizes_output(dev):
     assert np.array_equal(sizes.cpu().numpy(), want)
 
 
-def test_encode_long_underflow_runs(dev):
+def straddle_stream():
+    # packets whose pending-underflow counter runs into the thousands (datagen.straddle_packet) between ordinary
+    # ones, so that the lanes of a warp hit the encoders' rare paths at different steps, some not at all
     rng = np.random.default_rng(5)
-    data = rng.choice(np.array([127, 128], np.uint8), size=8192 * 40, p=[0.5, 0.5])
-    assert np.array_equal(dev_encode(dev, data), O.encode(data))
+    st = D.straddle_packet(8192)
+    parts = []
+    for p in range(70):
+        parts.append(st if p % 3 == 0 else st[: 8192 - 7 * p][::1] if p % 7 == 3 else
+                     rng.choice(np.array([127, 128], np.uint8), size=8192) if p % 3 == 1 else D.uniform(p, 8192))
+    parts = [np.resize(a, 8192) for a in parts]
+    return np.concatenate(parts + [st[:4097]])
+
+
+@pytest.mark.parametrize("path", ["auto", "fused", "ws"])
+def test_encode_long_underflow_runs(dev, path):
+    from gpuar_b200 import _lib
+    rng = np.random.default_rng(5)
+    _lib.set_option(_lib.OPT_ENCODE_PATH, {"auto": 0, "fused": 1, "ws": 2}[path])
+    try:
+        data = rng.choice(np.array([127, 128], np.uint8), size=8192 * 40, p=[0.5, 0.5])
+        assert np.array_equal(dev_encode(dev, data), O.encode(data))
+        data = straddle_stream()
+        assert np.array_equal(dev_encode(dev, data), O.encode(data))
+    finally:
+        _lib.set_option(_lib.OPT_ENCODE_PATH, 0)
 
 
 @pytest.mark.parametrize("path", ["fused", "ws"])
@@ -207,7 +228,7 @@ def test_both_decode_kernels_are_bit_exact(dev, path):
     rng = np.random.default_rng(11)
     cases = [make_input(VECTORS[name]) for name in SMALL]
     cases += [D.mixed(5, 8192 * 70 + 123), D.zeros(8192 * 3 + 1), D.uniform(9, 8192 * 40 - 1),
-              rng.choice(np.array([127, 128], np.uint8), size=8192 * 33)]
+              rng.choice(np.array([127, 128], np.uint8), size=8192 * 33), straddle_stream()]
     _lib.set_option(_lib.OPT_DECODE_PATH, {"latency": 1, "throughput": 2}[path])
     try:
         for data in cases:

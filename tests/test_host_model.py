@@ -19,13 +19,16 @@ SO = os.path.join(HERE, "_build", "libhost_model.so")
 @pytest.fixture(scope="module")
 def model():
     src = os.path.join(HERE, "host_model.cpp")
-    hdrs = [os.path.join(HERE, "..", "gpuar_b200", "csrc", h) for h in ("coder_math.h", "decode_math.h")]
+    hdrs = [os.path.join(HERE, "..", "gpuar_b200", "csrc", h) for h in ("coder_math.h", "decode_math.h", "encode_math.h")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(f) for f in [src] + hdrs):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", src, "-o", SO])
     lib = C.CDLL(SO)
     lib.host_model_encode_stream.restype = C.c_size_t
     lib.host_model_encode_stream.argtypes = [O._u8p, C.c_size_t, O._u8p, C.c_uint32]
+    lib.host_model_encode_stream_plain.restype = C.c_size_t
+    lib.host_model_encode_stream_plain.argtypes = [O._u8p, C.c_size_t, O._u8p, C.c_uint32]
+    lib.host_model_carry_events.restype = C.c_uint64
     lib.host_model_encode_stream_ws.restype = C.c_size_t
     lib.host_model_encode_stream_ws.argtypes = [O._u8p, C.c_size_t, O._u8p, C.c_uint32]
     lib.host_model_decode_packet.restype = C.c_uint32
@@ -45,10 +48,12 @@ def model():
     return lib
 
 
-def model_encode(lib, data, packet=8192, ws=False):
+def model_encode(lib, data, packet=8192, ws=False, plain=False):
     buf = np.zeros(O.n_packets(data.size, packet) * (packet + 512) + 64, np.uint8)
     src = data if data.size else np.zeros(1, np.uint8)
     fn = lib.host_model_encode_stream_ws if ws else lib.host_model_encode_stream
+    if plain:                              # encode_math.h: plain window, carry into the pending bits
+        fn = lib.host_model_encode_stream_plain
     return buf[: fn(O._ptr(src), data.size, O._ptr(buf), packet)].copy()
 
 
@@ -95,6 +100,7 @@ def test_kernel_math_matches_reference_golden(model, name):
     pay = model_encode(model, data)
     assert pay.size == rec["payload_bytes"] and md5(pay) == rec["payload_md5"]
     assert np.array_equal(model_encode(model, data, ws=True), pay)
+    assert np.array_equal(model_encode(model, data, plain=True), pay)
     assert np.array_equal(model_decode(model, pay, data.size), data)
     assert np.array_equal(model_decode(model, pay, data.size, early=True), data)
     assert np.array_equal(model_decode(model, pay, data.size, early=True, total=True), data)
@@ -109,6 +115,7 @@ def test_kernel_math_ragged_lengths(model, n):
         pay = model_encode(model, data)
         assert np.array_equal(pay, O.encode(data))
         assert np.array_equal(model_encode(model, data, ws=True), pay)
+        assert np.array_equal(model_encode(model, data, plain=True), pay)
         assert np.array_equal(model_decode(model, pay, n), data)
         assert np.array_equal(model_decode(model, pay, n, early=True), data)
         assert np.array_equal(model_decode(model, pay, n, early=True, total=True), data)
@@ -125,6 +132,7 @@ def test_kernel_math_other_packet_sizes(model, packet):
     pay = model_encode(model, data, packet)
     assert pay.size == rec["payload_bytes"] and md5(pay) == rec["payload_md5"]
     assert np.array_equal(model_encode(model, data, packet, ws=True), pay)
+    assert np.array_equal(model_encode(model, data, packet, plain=True), pay)
     assert np.array_equal(model_decode(model, pay, data.size), data)
     assert np.array_equal(model_decode(model, pay, data.size, early=True), data)
     assert np.array_equal(model_decode(model, pay, data.size, early=True, total=True), data)
@@ -136,12 +144,18 @@ def test_kernel_math_other_packet_sizes(model, packet):
 def test_kernel_math_long_underflow_runs(model):
     # two-symbol inputs straddling the midpoint keep the coder in the 01../10.. state
     rng = np.random.default_rng(5)
-    for _ in range(8):
-        data = rng.choice(np.array([127, 128], np.uint8), size=8192, p=[0.5, 0.5])
+    carries_before = model.host_model_carry_events()
+    straddle, max_pend = D.straddle_packet(8192, report=True)     # pending-underflow counter in the thousands
+    assert max_pend > 1000
+    for k in range(9):
+        data = straddle if k == 8 else rng.choice(np.array([127, 128], np.uint8), size=8192, p=[0.5, 0.5])
         pay = model_encode(model, data)
         assert np.array_equal(pay, O.encode(data))
         assert np.array_equal(model_encode(model, data, ws=True), pay)
+        assert np.array_equal(model_encode(model, data, plain=True), pay)
         assert np.array_equal(model_decode(model, pay, 8192), data)
         assert np.array_equal(model_decode(model, pay, 8192, early=True, total=True), data)
         for v in range(2):
             assert np.array_equal(model_decode(model, pay, 8192, v2=v), data)
+    # the plain-window encoder had to carry into words it had already stored (its rare path) on these inputs
+    assert model.host_model_carry_events() > carries_before
