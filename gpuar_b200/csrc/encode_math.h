@@ -62,6 +62,32 @@ GPUAR_HD void narrow_plain(EncState &st, uint32_t lo, uint32_t hi, uint32_t m, u
     inc = X >> so;
 }
 
+// The same step for the CODER warp of encode_ws.cu, which carries the range unnormalised by one halving
+// (narrow_lazy of coder_math.h: state R1, sx with range = R1 >> sx; the next step's multiplies start from R1
+// while the decision sx is still being computed).  The step's output travels to the BITS warp as one word:
+// inc in bits 0..16, t in bits 20..24 (handing X, E and sx over raw and letting BITS work out the shift was
+// measured too: BITS then paces the kernel, profiles/r2_encode_v2.md).  Zero is a step that moves nothing.
+//   state: Lp, R1, sx.   Start: Lp = 0, R1 = 65536, sx = 0.
+constexpr uint32_t kStepNone = 0u;
+GPUAR_HD uint32_t narrow_plain_lazy(uint32_t &Lp, uint32_t &R1, uint32_t &sx, uint32_t lo, uint32_t hi, uint32_t m, uint32_t sh)
+{
+    const uint32_t qa = (mulhi32(hi * R1, m) >> sh) >> sx;
+    const uint32_t qb = (mulhi32(lo * R1, m) >> sh) >> sx;
+    const uint32_t E = width_exponent(qa, qb);
+    const uint32_t X = Lp + qb;
+    const uint32_t A = funnel_r_wrap(X << 16, 0u, E);             // (X mod 2^16) << s1
+    R1 = funnel_r_wrap((qa - qb) << 16, 0u, E);
+    sx = ((A & 0x7FFFu) + R1 - 0x8001u) >> 15;
+    Lp = (A >> sx) & 0xFFFFu;
+    const uint32_t so = (E & 31u) + sx;                           // 16 - t
+    return (X >> so) + ((16u - so) << 20);
+}
+GPUAR_HD void step_unpack(uint32_t w, uint32_t &inc, uint32_t &t)
+{
+    inc = w & 0xFFFFFu;
+    t = w >> 20;
+}
+
 // Bit sink with carry: `acc` holds the nb newest bits of the stream as a number, plus possibly one carry bit
 // above them.  A 32-bit word is stored as soon as 48 bits are pending, so 16..47 stay behind.
 struct CarrySink {

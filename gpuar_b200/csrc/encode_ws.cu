@@ -1,21 +1,21 @@
 // encode_ws.cu -- warp-specialised variant of the encode kernel for inputs that cannot fill
 // the machine (a 64 MiB input is 8192 packets = 256 lane=packet warps for 592 warp schedulers).
 //
-// Same arithmetic as encode_kernel (coder_math.h), same output, but the stages of a symbol
-// step run in six different warps of a 192-thread CTA that owns 32 packets:
-//     warp 0  MODEL-A  tree levels 0-1               -> ring A (partial cum[s])
-//     warp 1  MODEL-B  tree level 2                  -> ring B (partial cum[s])
-//     warp 2  MODEL-D  tree level 3 (the leaves)     -> ring D (partial cum[s] | count[s] << 16)
-//     warp 3  FIELD    k, u and the bit field        -> ring F (pack_field descriptor)
-//     warp 4  BITS     bit sink                      -> the packet's slot
-//     warp 5  CODER    narrow_lazy (the chain)       -> ring C (L1 | U1 << 16)
+// Same arithmetic as encode_kernel (coder_math.h, encode_math.h), same output, but the stages of a symbol
+// step run in five different warps of a CTA that owns 32 packets:
+//     MODEL-A  tree levels 0-1               -> ring A (partial cum[s])
+//     MODEL-B  tree level 2                  -> ring B (partial cum[s])
+//     MODEL-D  tree level 3 (the leaves)     -> ring D (partial cum[s] | count[s] << 16)
+//     CODER    narrow_plain_lazy (the chain) -> ring C (the bits that left the window + carry | their count << 20)
+//     BITS     carry-propagating bit sink    -> the packet's slot
 // The tree levels are independent of each other given the symbol, so the model splits by
 // level.  Only CODER carries the serial dependence of arithmetic coding, and it carries the
-// minimum: the interval recurrence with its single normalisation (narrow_lazy); how the
-// total shift splits into matching-MSB and underflow shifts -- two count-leading-zeros --
-// is worked out by FIELD, which has no state at all, and everything of the emission that
-// depends on the pending-underflow counter by BITS.  CODER is the highest warp of the CTA
-// because the SM sub-partition arbiter favours the highest warp slot.
+// minimum: the interval recurrence with its single normalisation on the plain window of the lower
+// bound (encode_math.h).  The bit stream is the lower bound written out as one long number, so BITS
+// only shifts the step's bits into its accumulator and adds the carry -- there is no pending-underflow
+// counter and no warp that works out how the shift splits into matching and underflow shifts (round 1
+// had a sixth, stateless FIELD warp for that).  CODER is the highest warp of the CTA because the SM
+// sub-partition arbiter favours the highest warp slot.
 // Each warp keeps lane = packet, so per-packet state never crosses lanes; the rings are
 // double buffered per round of 32 positions and handed over with named barriers
 // (bar.arrive on the producer side, bar.sync on the consumer side).  The three model rings
@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "encode_math.h"
 #include "kernels.h"
 #include "shard.cuh"
 
@@ -35,22 +36,22 @@ namespace gpuar {
 
 constexpr uint32_t kRound = 32;
 constexpr uint32_t kCoderBlock = GPUAR_WS_CODER_BLOCK;
-// Role placement.  The CTA is launched with six or eight warps and a role map says what each one
-// does: nibble w of the map = role of warp w, 0xF = none (the warp exits at once).  Which roles
-// share a scheduler (SM sub-partition; warp index modulo 4 for a CTA alone on its SM) matters:
-// with one CTA per SM (up to 148 x 32 packets = 37 MiB, and every chunk of the host-buffer
-// pipeline) eight warps with the CODER chain alone on its scheduler take 118 instead of 128
-// cycles per step; with two or three CTAs per SM every eight-warp placement measured was slower
-// than the plain six-warp CTA (0.65-0.80 against 0.624 ms at 64 MiB; how the hardware spreads a
-// second CTA's warps over the sub-partitions is not the simple rule above), so that one stays
-// (profiles/r1_s2_ws_rolemap*.jsonl).  GPUAR_B200_WS_TUNE="warps,map_first,map_later" (hex maps)
-// overrides the choice for experiments; the CTAs of the first wave (one per SM) take map_first,
-// the others map_later.
+// Role placement.  The CTA is launched with five or eight warps and a role map says what each one
+// does: nibble w of the map = role of warp w (0 MODEL-A, 1 MODEL-B, 2 MODEL-D, 4 BITS, 5 CODER), 0xF = none
+// (the warp exits at once).  Which roles share a scheduler (SM sub-partition; warp index modulo 4 for a CTA
+// alone on its SM) matters (profiles/r2_encode_v2.md, 32 / 64 / 128 / 192 MiB in ms):
+//     eight warps, A+B | BITS | D | CODER      0.476  0.633  1.168  1.565    <- one CTA per SM (up to 37 MiB, and every
+//     eight warps, A | B+BITS | D | CODER      0.508  0.574  1.146  1.553       chunk of the host-buffer pipeline)
+//     five warps,  B+CODER | A | D | BITS      0.528  0.651  1.251  1.495    <- up to four CTAs per SM / above
+// (how the hardware spreads a second CTA's warps over the sub-partitions is not the simple modulo rule).
+// GPUAR_B200_WS_TUNE="warps,map_first,map_later" (hex maps) overrides the choice for experiments; the CTAs
+// of the first wave (one per SM) take map_first, the others map_later.
 constexpr uint32_t kWsMaxThreads = 256;
-constexpr uint32_t kMapSix = 0xFF543210u;       // warps 0-5 = roles 0-5: A+BITS | B+CODER | D | FIELD
-constexpr uint32_t kMapCoderAlone = 0x5F43F210u; // A+FIELD | B+BITS | D | CODER
+constexpr uint32_t kMapCompact = 0xFFF54201u;    // five warps: B+CODER | A | D | BITS
+constexpr uint32_t kMapCoderAlone = 0x5F4FF210u; // eight warps: A | B+BITS | D | CODER
+constexpr uint32_t kMapAllAlone = 0x5FF1F240u;   // eight warps: A+B | BITS | D | CODER
 #ifndef GPUAR_WS_SWAP_BD
-#define GPUAR_WS_SWAP_BD 0          // tuning knob: which of warps 1 / 2 takes level 2 and which the leaves
+#define GPUAR_WS_SWAP_BD 0          // tuning knob: which of the roles 1 / 2 takes level 2 and which the leaves
 #endif
 constexpr uint32_t kRoleB = GPUAR_WS_SWAP_BD ? 2u : 1u, kRoleD = GPUAR_WS_SWAP_BD ? 1u : 2u;
 
@@ -59,19 +60,18 @@ struct WsShared {
     uint32_t ring_a[2][kRound][32];      //  8192 B each (MODEL -> CODER)
     uint32_t ring_b[2][kRound][32];
     uint32_t ring_d[2][kRound][32];
-    uint32_t ring_c[2][kRound][32];      // CODER -> FIELD
-    uint2 ring_f[2][kRound][32];         // FIELD -> BITS (16384 B: two-word descriptors)
+    uint32_t ring_c[2][kRound][32];      // CODER -> BITS: one word per step (encode_math.h: narrow_plain_lazy)
     uint32_t stage[3][8][32];            // the model warps' input words of the current round
     uint32_t final_l[32];                // CODER -> BITS at the end of the packet
 };
 
-// Named barriers, id + buffer index; all sixteen are in use (the kernel has no __syncthreads,
-// so barrier 0 is free).  A "full" barrier is arrived at by the producer(s) and waited on by the
-// one consumer; an "empty" barrier the other way round.  The three model rings share their full
-// barrier (three producers + CODER = 128 threads) but are handed back one by one, so that
-// every barrier has exactly one waiting warp (which is also what compute-sanitizer's synccheck
-// expects: it reports warps that wait on one barrier from different instructions as divergent).
-enum : uint32_t { kInFull = 0, kInEmpty = 2 /* + 2 * role */, kCFull = 8, kCEmpty = 10, kFFull = 12, kFEmpty = 14 };
+// Named barriers, id + buffer index (the kernel has no __syncthreads, so barrier 0 is free).  A "full"
+// barrier is arrived at by the producer(s) and waited on by the one consumer; an "empty" barrier the other
+// way round.  The three model rings share their full barrier (three producers + CODER = 128 threads) but are
+// handed back one by one, so that every barrier has exactly one waiting warp (which is also what
+// compute-sanitizer's synccheck expects: it reports warps that wait on one barrier from different
+// instructions as divergent).
+enum : uint32_t { kInFull = 0, kInEmpty = 2 /* + 2 * role */, kCFull = 8, kCEmpty = 10 };
 constexpr uint32_t kInCount = 128;       // MODEL-A, MODEL-B, MODEL-D, CODER
 constexpr uint32_t kPairCount = 64;      // one producer warp + one consumer warp
 
@@ -151,7 +151,7 @@ __device__ __forceinline__ void model_warp(WsShared &sm, uint64_t *tree, const u
     }
 }
 
-__global__ void __launch_bounds__(kWsMaxThreads)
+__global__ void __launch_bounds__(kWsMaxThreads, 1)
 encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ slots, uint32_t slot_stride,
                  uint32_t *__restrict__ sizes, uint32_t n_packets, uint32_t packet, uint32_t map_first,
                  uint32_t map_later, uint32_t first_ctas, ShardTarget tg, uint64_t *__restrict__ acc)
@@ -178,7 +178,7 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
         model_warp<2>(sm, tree, src + off, len, min_len, rounds, lane);
     } else if (role == 5u) {
         // ------------------------------------------------------------ CODER
-        uint32_t L = 0, R1 = 65536u, sx = 0;                      // narrow_lazy state: range = R1 >> sx
+        uint32_t Lp = 0, R1 = 65536u, sx = 0;                     // narrow_plain_lazy state: range = R1 >> sx
         for (uint32_t r = 0; r < rounds; ++r) {
             const uint32_t b = r & 1u, i0 = r * kRound;
             uint32_t sh;
@@ -202,11 +202,8 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
                         m[j] = __shfl_sync(kFull, m_l, j0 + j);
                     }
 #pragma unroll
-                    for (uint32_t j = 0; j < kCoderBlock; ++j) {
-                        uint32_t L1, S1;
-                        narrow_lazy(L, R1, sx, lo[j], hi[j], m[j], sh, L1, S1);
-                        sm.ring_c[b][j0 + j][lane] = pack_bounds(L1, S1);
-                    }
+                    for (uint32_t j = 0; j < kCoderBlock; ++j)
+                        sm.ring_c[b][j0 + j][lane] = narrow_plain_lazy(Lp, R1, sx, lo[j], hi[j], m[j], sh);
                 }
             } else {
 #pragma unroll 1
@@ -214,12 +211,8 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
                     const uint32_t m = __shfl_sync(kFull, m_l, j);
                     const uint32_t pd = sm.ring_d[b][j][lane];
                     const uint32_t lo = sm.ring_a[b][j][lane] + sm.ring_b[b][j][lane] + (pd & 0xFFFFu);
-                    uint32_t c = 0;
-                    if (i0 + j < len) {
-                        uint32_t L1, S1;
-                        narrow_lazy(L, R1, sx, lo, lo + (pd >> 16), m, sh, L1, S1);
-                        c = pack_bounds(L1, S1);
-                    }
+                    uint32_t c = kStepNone;                        // no bits, no carry
+                    if (i0 + j < len) c = narrow_plain_lazy(Lp, R1, sx, lo, lo + (pd >> 16), m, sh);
                     sm.ring_c[b][j][lane] = c;
                 }
             }
@@ -228,97 +221,43 @@ encode_ws_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict_
                 bar_arrive_raw<kPairCount>(kInEmpty + 2u + b);
                 bar_arrive_raw<kPairCount>(kInEmpty + 4u + b);
             }
-            if (r + 1u == rounds) sm.final_l[lane] = L;            // reaches BITS through the two hand-overs below
+            if (r + 1u == rounds) sm.final_l[lane] = Lp;           // reaches BITS through the hand-over below
             bar_arrive<kPairCount>(kCFull + b);
-        }
-    } else if (role == 3u) {
-        // ------------------------------------------------------------ FIELD (stateless)
-        for (uint32_t r = 0; r < rounds; ++r) {
-            const uint32_t b = r & 1u, i0 = r * kRound;
-            const bool full = i0 + kRound <= min_len;
-            bar_sync<kPairCount>(kCFull + b);
-            if (r >= 2u) bar_sync<kPairCount>(kFEmpty + b);
-            if (full) {
-                // straight-line blocks of eight independent steps: the count-leading-zeros latencies overlap
-#pragma unroll 1
-                for (uint32_t j0 = 0; j0 < kRound; j0 += 8u) {
-                    uint32_t c[8];
-#pragma unroll
-                    for (uint32_t j = 0; j < 8u; ++j) c[j] = sm.ring_c[b][j0 + j][lane];
-#pragma unroll
-                    for (uint32_t j = 0; j < 8u; ++j) {
-                        uint32_t k, u;
-                        shifts_of(c[j] & 0xFFFFu, c[j] >> 16, k, u);
-                        const FieldDesc d = pack_field(k, u, c[j]);
-                        sm.ring_f[b][j0 + j][lane] = make_uint2(d.w0, d.w1);
-                    }
-                }
-            } else {
-#pragma unroll 1
-                for (uint32_t j = 0; j < kRound; ++j) {
-                    const uint32_t c = sm.ring_c[b][j][lane];
-                    uint32_t k, u;
-                    shifts_of(c & 0xFFFFu, c >> 16, k, u);
-                    const FieldDesc d = pack_field(k, u, c);
-                    sm.ring_f[b][j][lane] = (i0 + j < len) ? make_uint2(d.w0, d.w1) : make_uint2(0u, 0u);
-                }
-            }
-            if (r + 2u < rounds) bar_arrive<kPairCount>(kCEmpty + b);
-            bar_arrive<kPairCount>(kFFull + b);
         }
     } else if (role == 4u) {
         // ------------------------------------------------------------ BITS
-        uint32_t pend = 0;
         uint8_t *const slot = slots + (size_t)my * slot_stride;
-        BitSink out;
-        out.acc = 0;
-        out.nb = 0;
-        out.widx = 0;
-        out.wcap = mine ? ((slot_stride - kHdr) >> 2) : 0u;
-        out.words = reinterpret_cast<uint32_t *>(slot + kHdr);
+        CarrySink out;
+        out.start(reinterpret_cast<uint32_t *>(slot + kHdr), mine ? ((slot_stride - kHdr) >> 2) : 0u);
         for (uint32_t r = 0; r < rounds; ++r) {
-            const uint32_t b = r & 1u, i0 = r * kRound;
-            const bool full = i0 + kRound <= min_len;
-            bar_sync<kPairCount>(kFFull + b);
-            if (full) {
-                // four steps per block.  The rare long-underflow path needs pend > 16 at a step
-                // with k != 0; pend grows by at most the u's of the group, so one warp-uniform
-                // vote on (pend + sum of u) covers the whole group and the common block has no
-                // branch at all: its four ring loads issue together.  The rare block reads the
-                // ring again rather than indexing the four registers (which would put them on
-                // the stack for the common block too).
+            const uint32_t b = r & 1u;
+            bar_sync<kPairCount>(kCFull + b);
+            // four steps per block: their ring loads issue together.  A step past the end of a lane's packet is a
+            // kStepNone word (no bits, no carry), so the ragged rounds need no predicate.  A carry that leaves the sink
+            // (through at least 16 pending one-bits) is added to the words already stored, under one vote.
 #pragma unroll 1
-                for (uint32_t j0 = 0; j0 < kRound; j0 += 4u) {
-                    const uint2 f0 = sm.ring_f[b][j0][lane], f1 = sm.ring_f[b][j0 + 1u][lane],
-                                f2 = sm.ring_f[b][j0 + 2u][lane], f3 = sm.ring_f[b][j0 + 3u][lane];
-                    const uint32_t usum = (f0.x >> 28) + (f1.x >> 28) + (f2.x >> 28) + (f3.x >> 28);
-                    if (__any_sync(kFull, pend + usum > 16u)) {
-#pragma unroll 1
-                        for (uint32_t j = 0; j < 4u; ++j) {
-                            const uint2 f = sm.ring_f[b][j0 + j][lane];
-                            emit_packed_any(out, pend, FieldDesc{f.x, f.y});
-                        }
-                    } else {
-                        emit_packed(out, pend, FieldDesc{f0.x, f0.y});
-                        emit_packed(out, pend, FieldDesc{f1.x, f1.y});
-                        emit_packed(out, pend, FieldDesc{f2.x, f2.y});
-                        emit_packed(out, pend, FieldDesc{f3.x, f3.y});
+            for (uint32_t j0 = 0; j0 < kRound; j0 += 4u) {
+                uint32_t c[4];
+#pragma unroll
+                for (uint32_t j = 0; j < 4u; ++j) c[j] = sm.ring_c[b][j0 + j][lane];
+#pragma unroll
+                for (uint32_t j = 0; j < 4u; ++j) {
+                    uint32_t inc, t;
+                    step_unpack(c[j], inc, t);
+                    const uint32_t stored = out.widx;
+                    const bool carry = out.push(inc, t);
+                    if (__any_sync(kFull, carry)) {
+                        if (carry) out.carry_into_stored(stored);
                     }
                 }
-            } else {
-#pragma unroll 1
-                for (uint32_t j = 0; j < kRound; ++j) {
-                    const uint2 f = sm.ring_f[b][j][lane];
-                    if (field_valid(FieldDesc{f.x, f.y})) emit_packed_any(out, pend, FieldDesc{f.x, f.y});
-                }
             }
-            if (r + 2u < rounds) bar_arrive<kPairCount>(kFEmpty + b);
+            if (r + 2u < rounds) bar_arrive<kPairCount>(kCEmpty + b);
         }
-        // final_l: written by CODER before its last "C full", which FIELD waited for before its last
-        // "F full", which this warp waited for in the last round (release/acquire chain at CTA scope)
+        // final_l: written by CODER before its last "C full", which this warp waited for in the last round
+        // (release/acquire chain at CTA scope)
         uint32_t comp = 0;
         if (mine) {
-            comp = finish_packet(out, sm.final_l[lane], pend, slot, len);
+            comp = finish_packet_plain(out, sm.final_l[lane], slot, len);
             if (sizes) sizes[my] = comp;
         }
         if (tg.world > 1u) {                                      // sharded encode: this rank's total for the other ranks
@@ -350,11 +289,13 @@ cudaError_t launch_encode_slots_ws(const uint8_t *d_in, size_t n, uint8_t *d_slo
         Tune t{0, 0, 0};
         if (const char *e = getenv("GPUAR_B200_WS_TUNE")) {
             unsigned w = 0, a = 0, b = 0;
-            if (sscanf(e, "%u,%x,%x", &w, &a, &b) == 3 && (w == 6 || w == 8)) t = Tune{w, a, b};
+            if (sscanf(e, "%u,%x,%x", &w, &a, &b) == 3 && w >= 5 && w <= 8) t = Tune{w, a, b};
         }
         return t;
     }();
-    Tune t = ctas <= (uint32_t)sms ? Tune{8, kMapCoderAlone, kMapCoderAlone} : Tune{6, kMapSix, kMapSix};
+    Tune t = ctas <= (uint32_t)sms        ? Tune{8, kMapAllAlone, kMapAllAlone}
+             : ctas <= 4u * (uint32_t)sms ? Tune{8, kMapCoderAlone, kMapCoderAlone}
+                                          : Tune{5, kMapCompact, kMapCompact};
     if (forced.warps) t = forced;
     encode_ws_kernel<<<ctas, 32u * t.warps, sizeof(WsShared), st>>>(d_in, n, d_slots, slot_stride, d_sizes, packets,
                                                                      packet, t.first, t.later, (uint32_t)sms, tg, d_acc);

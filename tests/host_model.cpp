@@ -40,24 +40,20 @@ uint32_t host_model_encode_packet(const uint8_t *x, uint32_t n, uint8_t *slot, u
     return finish_packet(out, L, pend, slot, n);
 }
 
-// the same packet through the stages of encode_ws_kernel: three model warps (levels 0-1, 2, 3),
-// CODER on the single-normalisation step, FIELD (k, u, packed descriptor), BITS
+// the same packet through the stages of encode_ws_kernel: three model warps (levels 0-1, 2, 3), CODER on the
+// plain window with the lazily normalised range, one word per step to BITS
 uint32_t host_model_encode_packet_ws(const uint8_t *x, uint32_t n, uint8_t *slot, uint32_t slot_bytes)
 {
     std::vector<uint64_t> tree(kTreeStored);
     uint64_t root;
     enc_tree_init(root, tree.data(), 1);
-    uint32_t L = 0, R = 65536, sx = 0, pend = 0;
-    BitSink out;
-    out.acc = 0;
-    out.nb = 0;
-    out.widx = 0;
-    out.wcap = (slot_bytes - kHdr) >> 2;
-    out.words = reinterpret_cast<uint32_t *>(slot + kHdr);
+    uint32_t Lp = 0, R = 65536, sx = 0;
+    CarrySink out;
+    out.start(reinterpret_cast<uint32_t *>(slot + kHdr), (slot_bytes - kHdr) >> 2);
     for (uint32_t i = 0; i < n; ++i) {
         uint32_t sh;
         const uint32_t m = magic_for(256u + i, sh);
-        uint32_t cnt, L1, S1, k, u;
+        uint32_t cnt;
         // the model warps take their symbols four at a time from one input word
         uint32_t word = 0;
         memcpy(&word, x + (i & ~3u), (n - (i & ~3u)) < 4u ? (n - (i & ~3u)) : 4u);
@@ -66,13 +62,13 @@ uint32_t host_model_encode_packet_ws(const uint8_t *x, uint32_t n, uint8_t *slot
         const uint32_t lo_d = tree_encode_leaf_word(tree.data(), 1, word_fields_leaf(word), i & 3u, cnt);
         const uint32_t pd = cnt * 65536u + lo_d;
         const uint32_t lo = pa + pb + (pd & 0xFFFFu);
-        narrow_lazy(L, R, sx, lo, lo + (pd >> 16), m, sh, L1, S1);
-        const uint32_t c = pack_bounds(L1, S1);                    // ring C entry
-        const uint32_t U1 = c >> 16;
-        shifts_of(c & 0xFFFFu, U1, k, u);
-        emit_packed_any(out, pend, pack_field(k, u, c));
+        const uint32_t c = narrow_plain_lazy(Lp, R, sx, lo, lo + (pd >> 16), m, sh);   // ring C entry
+        uint32_t inc, t;
+        step_unpack(c, inc, t);
+        const uint32_t before = out.widx;
+        if (out.push(inc, t)) out.carry_into_stored(before);
     }
-    return finish_packet(out, L, pend, slot, n);
+    return finish_packet_plain(out, Lp, slot, n);
 }
 
 // how often host_model_encode_packet_plain had to carry into words it had already stored (the rare path of the
