@@ -3,8 +3,8 @@
 //
 // Same arithmetic as the reference (getUnscaledCode src/gpuar_kernel.cu:703-716,
 // getSymbolFromProbability :727-763, applySymbolRange :256-288, readEncodedBits :787-836); what
-// changed against the first-generation step (coder_math.h: tree_decode / tree_decode_spec_range +
-// narrow_total + advance_code_total) is the bookkeeping around it -- the instruction count and, for
+// changed against the first-generation step (round 1: quotient, packed levels that hand the room above the
+// target down, code register with its underflow flip) is the bookkeeping around it -- the instruction count and, for
 // a lone warp, the length of the dependent chain are what bound the decoder (profiles/r2_decode_v2.md):
 //   * the decoder carries D = code - lower bound (mod 2^16) instead of `code`: the numerator of the
 //     quotient is D * T + T - 1 directly, and an underflow step flips bit 15 of the code AND drops
@@ -111,11 +111,11 @@ GPUAR_HD uint32_t leaf_level(uint32_t &lo, uint32_t &hi, uint32_t rem, uint32_t 
 // State of one packet's decoder between symbols.
 struct DecState {
     uint32_t D;          // (code - lower bound) mod 2^16
-    uint32_t L, R;       // lower bound (15 bits) and range, as narrow_total keeps them
+    uint32_t L, R;       // lower bound (15 bits) and range
 };
 
-// Interval narrowing + renormalisation + the next bits, on (D, L, R): narrow_total's arithmetic with the
-// code register folded into D.
+// Interval narrowing with the single normalisation (coder_math.h) + the next bits, on (D, L, R): the code
+// register is folded into D.
 GPUAR_HD void narrow_track(DecState &st, uint32_t lo, uint32_t hi, uint32_t m, uint32_t sh, BitSource &in)
 {
     const uint32_t qa = div_total(hi * st.R, m, sh);

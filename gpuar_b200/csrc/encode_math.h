@@ -44,7 +44,7 @@ struct EncState {
     uint32_t R;          // range = upper - lower + 1
 };
 
-// Interval narrowing with a single normalisation (as narrow_total of coder_math.h) on the plain window.
+// Interval narrowing with a single normalisation (derivation in coder_math.h) on the plain window.
 //   out: inc = the t bits that leave the window plus the carry (t + 1 bits), t = total shift (0..16)
 GPUAR_HD void narrow_plain(EncState &st, uint32_t lo, uint32_t hi, uint32_t m, uint32_t sh, uint32_t &inc, uint32_t &t)
 {
@@ -63,8 +63,8 @@ GPUAR_HD void narrow_plain(EncState &st, uint32_t lo, uint32_t hi, uint32_t m, u
 }
 
 // The same step for the CODER warp of encode_ws.cu, which carries the range unnormalised by one halving
-// (narrow_lazy of coder_math.h: state R1, sx with range = R1 >> sx; the next step's multiplies start from R1
-// while the decision sx is still being computed).  The step's output travels to the BITS warp as one word:
+// (state R1, sx with range = R1 >> sx: floor(c * (R1 >> sx) / T) = floor(c * R1 / T) >> sx, R1 being even whenever
+// sx = 1, so the next step's multiplies start from R1 while the decision sx is still being computed).  The step's output travels to the BITS warp as one word:
 // inc in bits 0..16, t in bits 20..24 (handing X, E and sx over raw and letting BITS work out the shift was
 // measured too: BITS then paces the kernel, profiles/r2_encode_v2.md).  Zero is a step that moves nothing.
 //   state: Lp, R1, sx.   Start: Lp = 0, R1 = 65536, sx = 0.

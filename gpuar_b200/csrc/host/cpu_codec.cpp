@@ -4,36 +4,37 @@
 #include <vector>
 
 #include "../coder_math.h"
+#include "../decode_math.h"
+#include "../encode_math.h"
 
 namespace gip {
 
 using namespace gpuar;
 
+// The explicit CPU mode of the command line (--host; the reference's CPUCompressor, src/cpu_compressor.cpp): the
+// same closed-form steps the kernels run (encode_math.h / decode_math.h), one packet at a time.
 std::uint32_t cpuEncodePacket(const std::uint8_t *in, std::uint32_t n, std::uint8_t *slot)
 {
     std::uint64_t tree[kTreeStored], root;
     enc_tree_init(root, tree, 1);
-    std::uint32_t L = 0, V = 0, pend = 0;
-    BitSink out;
-    out.acc = 0;
-    out.nb = 0;
-    out.widx = 0;
-    out.wcap = (kSlot - kHdr) >> 2;
-    out.words = reinterpret_cast<std::uint32_t *>(slot + kHdr);
+    EncState st{0u, 65536u};
+    CarrySink out;
+    out.start(reinterpret_cast<std::uint32_t *>(slot + kHdr), (kSlot - kHdr) >> 2);
     for (std::uint32_t i = 0; i < n; ++i) {
-        std::uint32_t sh, lo, cnt, k, u, U1;
+        std::uint32_t sh, lo, cnt, inc, t;
         const std::uint32_t m = magic_for(256u + i, sh);
         tree_encode(root, tree, 1, in[i], lo, cnt);
-        narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
-        emit_symbol(out, pend, k, u, U1);
+        narrow_plain(st, lo, lo + cnt, m, sh, inc, t);
+        const std::uint32_t stored = out.widx;
+        if (out.push(inc, t)) out.carry_into_stored(stored);
     }
-    return finish_packet(out, L, pend, slot, n);
+    return finish_packet_plain(out, st.Lp, slot, n);
 }
 
 std::uint32_t cpuDecodePacket(const std::uint8_t *pkt, std::uint8_t *out)
 {
     std::uint64_t tree[kTreeStored], root;
-    tree_init(root, tree, 1);
+    dec_tree_init(root, tree, 1);
     const std::uint32_t raw = (std::uint32_t)pkt[2] | ((std::uint32_t)pkt[3] << 8);
     const std::uint8_t *p = pkt + kHdr;
     auto word = [&]() {                                   // next 4 stream bytes, first byte = most significant
@@ -44,17 +45,16 @@ std::uint32_t cpuDecodePacket(const std::uint8_t *pkt, std::uint8_t *out)
     BitSource in;
     const std::uint64_t w0 = word(), w1 = word();
     in.start((w0 << 32) | w1, 64u);
-    std::uint32_t code = in.take(16u);
+    DecState st;
+    st.D = in.take(16u);
+    st.L = 0;
+    st.R = 65536u;
     if (in.hungry()) in.feed(word());
-    std::uint32_t L = 0, V = 0;
     for (std::uint32_t i = 0; i < raw && i < kPacket; ++i) {
         const std::uint32_t T = 256u + i;
-        std::uint32_t sh, lo, cnt, k, u, U1;
+        std::uint32_t sh;
         const std::uint32_t m = magic_for(T, sh);
-        const std::uint32_t s = tree_decode(root, tree, 1, unscale(code, L, V, T), T, lo, cnt);
-        out[i] = (std::uint8_t)s;
-        narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
-        code = advance_code(code, k, u, in);
+        out[i] = (std::uint8_t)decode_step(st, root, tree, 1, T, m, sh, in);
         if (in.hungry()) in.feed(word());
     }
     return raw < kPacket ? raw : kPacket;

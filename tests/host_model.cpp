@@ -1,9 +1,10 @@
 // host_model.cpp -- CPU emulation of the CUDA kernels' data flow, built with g++ from the
-// SAME arithmetic source the kernels use (gpuar_b200/csrc/coder_math.h).  Test
-// infrastructure: it lets `pytest -m "not gpu"` check the closed forms (reciprocal
-// division, renormalisation, bit packing, the 4-ary model tree with its packed compares
-// and byte permutes, the float-estimated divide) against the oracle without a GPU.  Both
-// kernels are lane = packet, so one lane is emulated at a time.
+// SAME arithmetic source the kernels use (gpuar_b200/csrc/coder_math.h, encode_math.h,
+// decode_math.h).  Test infrastructure: it lets `pytest -m "not gpu"` check the closed forms
+// (reciprocal division, single-normalisation renormalisation, the carry-propagating bit output,
+// the 4-ary model tree with its packed compares and byte permutes, the float-estimated divide,
+// the multiplicative tree descent) against the oracle without a GPU.  All kernels are
+// lane = packet, so one lane is emulated at a time.
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -15,30 +16,6 @@
 using namespace gpuar;
 
 extern "C" {
-
-// encode one packet exactly as a lane of encode_kernel does; returns compLen
-uint32_t host_model_encode_packet(const uint8_t *x, uint32_t n, uint8_t *slot, uint32_t slot_bytes)
-{
-    std::vector<uint64_t> tree(kTreeStored);
-    uint64_t root;
-    enc_tree_init(root, tree.data(), 1);
-    uint32_t L = 0, V = 0, pend = 0;
-    BitSink out;
-    out.acc = 0;
-    out.nb = 0;
-    out.widx = 0;
-    out.wcap = (slot_bytes - kHdr) >> 2;
-    out.words = reinterpret_cast<uint32_t *>(slot + kHdr);
-    for (uint32_t i = 0; i < n; ++i) {
-        uint32_t sh;
-        const uint32_t m = magic_for(256u + i, sh);
-        uint32_t lo, cnt, k, u, U1;
-        tree_encode(root, tree.data(), 1, x[i], lo, cnt);
-        narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
-        emit_symbol(out, pend, k, u, U1);
-    }
-    return finish_packet(out, L, pend, slot, n);
-}
 
 // the same packet through the stages of encode_ws_kernel: three model warps (levels 0-1, 2, 3), CODER on the
 // plain window with the lazily normalised range, one word per step to BITS
@@ -71,13 +48,14 @@ uint32_t host_model_encode_packet_ws(const uint8_t *x, uint32_t n, uint8_t *slot
     return finish_packet_plain(out, Lp, slot, n);
 }
 
-// how often host_model_encode_packet_plain had to carry into words it had already stored (the rare path of the
+// how often host_model_encode_packet had to carry into words it had already stored (the rare path of the
 // kernels): lets the tests assert that their long-underflow inputs really exercise it
 static uint64_t g_carry_events = 0;
 uint64_t host_model_carry_events(void) { return g_carry_events; }
 
-// the second-generation coder + bit output (encode_math.h): plain window, carry into the pending bits
-uint32_t host_model_encode_packet_plain(const uint8_t *x, uint32_t n, uint8_t *slot, uint32_t slot_bytes)
+// encode one packet exactly as a lane of encode_kernel does (encode_math.h: plain window, carry into the
+// pending bits); returns compLen
+uint32_t host_model_encode_packet(const uint8_t *x, uint32_t n, uint8_t *slot, uint32_t slot_bytes)
 {
     std::vector<uint64_t> tree(kTreeStored);
     uint64_t root;
@@ -114,11 +92,6 @@ static size_t encode_stream_with(uint32_t (*enc)(const uint8_t *, uint32_t, uint
     return pos;
 }
 
-size_t host_model_encode_stream_plain(const uint8_t *in, size_t n, uint8_t *payload, uint32_t packet)
-{
-    return encode_stream_with(host_model_encode_packet_plain, in, n, payload, packet);
-}
-
 size_t host_model_encode_stream_ws(const uint8_t *in, size_t n, uint8_t *payload, uint32_t packet)
 {
     return encode_stream_with(host_model_encode_packet_ws, in, n, payload, packet);
@@ -126,86 +99,13 @@ size_t host_model_encode_stream_ws(const uint8_t *in, size_t n, uint8_t *payload
 
 size_t host_model_encode_stream(const uint8_t *in, size_t n, uint8_t *payload, uint32_t packet)
 {
-    std::vector<uint8_t> slot(packet + 512 + 16);
-    size_t pos = 0;
-    for (size_t off = 0; off < n; off += packet) {
-        const uint32_t m = (uint32_t)(n - off < packet ? n - off : packet);
-        const uint32_t len = host_model_encode_packet(in + off, m, slot.data(), packet + 512);
-        memcpy(payload + pos, slot.data(), len);
-        pos += len;
-    }
-    return pos;
+    return encode_stream_with(host_model_encode_packet, in, n, payload, packet);
 }
 
-// decode the packet at byte offset `off` of a padded, 4-byte aligned payload exactly as a
-// lane of decode_kernel does; returns bytes produced
-static uint32_t decode_packet(const uint8_t *payload, size_t readable, size_t off, uint8_t *out, bool early,
-                              bool total = false)
-{
-    std::vector<uint64_t> tree(kTreeStored);
-    uint64_t root;
-    tree_init(root, tree.data(), 1);
-    const uint32_t *const words = reinterpret_cast<const uint32_t *>(payload);
-    const uint32_t *const wend = words + (readable >> 2) - 1;
-    auto word = [&](const uint32_t *p) { return bswap32(*(p < wend ? p : wend)); };
-    const uint32_t raw = (uint32_t)payload[off + 2] | ((uint32_t)payload[off + 3] << 8);
-    const size_t sp = off + kHdr;
-    const uint32_t *wp = words + (sp >> 2);
-    const uint32_t skip = 8u * (uint32_t)(sp & 3u);
-    BitSource in;
-    const uint64_t w0 = word(wp);
-    ++wp;
-    const uint64_t w1 = word(wp);
-    ++wp;
-    in.start(((w0 << 32) | w1) << skip, 64u - skip);
-    uint32_t ahead = word(wp);
-    uint32_t code = in.take(16u);
-    if (in.hungry()) { in.feed(ahead); ++wp; ahead = word(wp); }
-    uint32_t L = 0, V = 0;
-    for (uint32_t i = 0; i < raw; ++i) {
-        const uint32_t T = 256u + i;
-        uint32_t sh;
-        const uint32_t m = magic_for(T, sh);
-        uint32_t lo, cnt;
-        if (total && i == 0) V = 65536u;                           // V holds the range in this variant
-        const uint32_t range = total ? V : 65536u - V - L;
-        const uint32_t s = early ? tree_decode_early_range(root, tree.data(), 1, code, L, range, T, lo, cnt)
-                                 : tree_decode(root, tree.data(), 1, unscale_range(code, L, range, T), T, lo, cnt);
-        out[i] = (uint8_t)s;
-        if (total) {
-            uint32_t L1, S1, t, As;
-            narrow_total(L, V, lo, lo + cnt, m, sh, L1, S1, t, As);
-            code = advance_code_total(code, t, As, in);
-        } else {
-            uint32_t k, u, U1;
-            narrow_renorm(L, V, lo, lo + cnt, m, sh, k, u, U1);
-            code = advance_code(code, k, u, in);
-        }
-        if (in.hungry()) { in.feed(ahead); ++wp; ahead = word(wp); }
-    }
-    return raw;
-}
-
-uint32_t host_model_decode_packet(const uint8_t *payload, size_t readable, size_t off, uint8_t *out)
-{
-    return decode_packet(payload, readable, off, out, false);
-}
-
-// the latency variant (multiplicative top levels) used by decode_kernel<true>
-uint32_t host_model_decode_packet_early(const uint8_t *payload, size_t readable, size_t off, uint8_t *out)
-{
-    return decode_packet(payload, readable, off, out, true);
-}
-
-// both with the single-normalisation step (decode_kernel with GPUAR_DEC_TOTAL_*)
-uint32_t host_model_decode_packet_total(const uint8_t *payload, size_t readable, size_t off, uint8_t *out, int early)
-{
-    return decode_packet(payload, readable, off, out, early != 0, true);
-}
-
-// the second-generation decoder step (decode_math.h) exactly as a lane of decode_kernel runs it:
-// variant 0 = throughput (decode_step), 1 = latency (decode_step_latency)
-uint32_t host_model_decode_packet_v2(const uint8_t *payload, size_t readable, size_t off, uint8_t *out, int variant)
+// decode the packet at byte offset `off` of a padded, 4-byte aligned payload exactly as a lane of
+// decode_kernel does (decode_math.h); variant 0 = throughput (decode_step), 1 = latency
+// (decode_step_latency); returns bytes produced
+uint32_t host_model_decode_packet(const uint8_t *payload, size_t readable, size_t off, uint8_t *out, int variant)
 {
     std::vector<uint64_t> tree(kTreeStored);
     std::vector<Quad> l1(4);
@@ -266,8 +166,11 @@ uint64_t host_model_check_division(uint32_t max_n, uint32_t packet)
     return bad;
 }
 
-// narrow_renorm against the reference's bit-at-a-time loop (gpuar_kernel.cu:256-288, 321-367) on
-// random reachable states: returns the number of mismatches in (L, U, k, u)
+// The steps of the kernels against the reference's bit-at-a-time loops (gpuar_kernel.cu:256-288, 321-367,
+// 787-836) on random reachable states: returns the number of mismatches.  Checked per state:
+//   narrow_renorm (first generation: k, u, both bounds), narrow_plain and narrow_plain_lazy (encoders: plain
+//   window with and without pending underflow bits, total shift, new range, the bits that leave the window),
+//   narrow_track and narrow_track_products (decoders: code - lower bound, lower bound, range, bit window).
 uint64_t host_model_check_renorm(uint64_t seed, uint32_t count, uint32_t packet)
 {
     uint64_t bad = 0, x = seed * 0x9E3779B97F4A7C15ull + 1;
@@ -283,36 +186,55 @@ uint64_t host_model_check_renorm(uint64_t seed, uint32_t count, uint32_t packet)
         uint32_t cl = (uint32_t)(rnd() % T), ch = cl + 1u + (uint32_t)(rnd() % (T - cl));
         if (n & 1u) ch = cl + 1u;                                  // narrow symbols stress the shifts
         if (ch > T) ch = T;
-        // reference arithmetic
-        uint32_t range = hi16 - lo16 + 1u;
+        // reference arithmetic, encoder and decoder side (the decoder's code lies inside the symbol's interval)
+        const uint32_t range = hi16 - lo16 + 1u;
         uint16_t U = (uint16_t)(lo16 + (uint16_t)(ch * range / T) - 1u), Lr = (uint16_t)(lo16 + (uint16_t)(cl * range / T));
-        const uint16_t U1ref = U;
-        uint32_t kk = 0, uu = 0;
+        const uint16_t U1ref = U, L1ref = Lr;
+        const uint32_t code0 = L1ref + (uint32_t)(rnd() % ((uint32_t)U1ref - L1ref + 1u));
+        const uint64_t window = rnd();                             // the next 64 stream bits
+        uint16_t code = (uint16_t)code0;
+        uint32_t kk = 0, uu = 0, taken = 0;
         for (;;) {
             if (((U ^ Lr) & 0x8000u) == 0) { ++kk; }
-            else if ((Lr & 0x4000u) && !(U & 0x4000u)) { ++uu; Lr &= 0x3FFFu; U |= 0x4000u; }
+            else if ((Lr & 0x4000u) && !(U & 0x4000u)) { ++uu; Lr &= 0x3FFFu; U |= 0x4000u; code ^= 0x4000u; }
             else break;
             Lr = (uint16_t)(Lr << 1);
             U = (uint16_t)((U << 1) | 1u);
+            code = (uint16_t)((code << 1) | (uint32_t)((window >> (63u - taken)) & 1u));
+            ++taken;
         }
-        uint32_t L = lo16, V = (~hi16) & 0xFFFFu, sh, k, u, U1;
+        const uint32_t new_range = (uint32_t)U - Lr + 1u;
+        uint32_t sh;
         const uint32_t m = magic_for(T, sh);
-        narrow_renorm(L, V, cl, ch, m, sh, k, u, U1);
-        bad += (L != Lr) || ((V ^ 0xFFFFu) != U) || (k != kk) || (u != uu) || (U1 != U1ref);
-        // the single-normalisation form of the same step (narrow_total + shifts_of)
-        uint32_t L2 = lo16, R2 = hi16 - lo16 + 1u, L1, S1, t, As, k2, u2;
-        narrow_total(L2, R2, cl, ch, m, sh, L1, S1, t, As);
-        const uint32_t U1b = S1 - 1u;
-        shifts_of(L1, U1b, k2, u2);
-        bad += (L2 != Lr) || (R2 != (uint32_t)U - Lr + 1u) || (U1b != U1ref) || (k2 != kk) || (u2 != uu);
-        bad += (t != kk + uu) || (((As >> 15) & 1u) != (uu ? 1u : 0u));
-        // and the lazy form, entered with the range held as is (sx = 0) or doubled (sx = 1)
-        for (uint32_t pre = 0; pre < 2u; ++pre) {
-            uint32_t L3 = lo16, R3 = (hi16 - lo16 + 1u) << pre, s3 = pre, L1c, S1c;
-            narrow_lazy(L3, R3, s3, cl, ch, m, sh, L1c, S1c);
-            bad += (L3 != Lr) || ((R3 >> s3) != (uint32_t)U - Lr + 1u) || (L1c != L1) || (S1c != U1ref + 1u) ||
-                   (s3 && (R3 & 1u)) || R3 <= 32768u || R3 > 65536u ||
-                   pack_bounds(L1c, S1c) != (L1 | ((uint32_t)U1ref << 16));
+        {   // first generation
+            uint32_t L = lo16, V = (~hi16) & 0xFFFFu, k, u, U1;
+            narrow_renorm(L, V, cl, ch, m, sh, k, u, U1);
+            bad += (L != Lr) || ((V ^ 0xFFFFu) != U) || (k != kk) || (u != uu) || (U1 != U1ref);
+        }
+        for (uint32_t pf = 0; pf < 2u; ++pf) {                     // encoders: without / with pending underflow bits
+            const uint32_t X = (pf << 15) + L1ref;
+            const uint32_t want_top = uu ? 1u : kk ? 0u : pf;
+            EncState st{lo16 | (pf << 15), range};
+            uint32_t inc, t;
+            narrow_plain(st, cl, ch, m, sh, inc, t);
+            bad += (t != kk + uu) || (st.R != new_range) || ((st.Lp & 0x7FFFu) != Lr) || ((st.Lp >> 15) != want_top) ||
+                   (inc != X >> (16u - t));
+            for (uint32_t pre = 0; pre < 2u; ++pre) {              // the range held as is (sx = 0) or doubled (sx = 1)
+                uint32_t Lp = lo16 | (pf << 15), R1 = range << pre, sx = pre, inc2, t2;
+                step_unpack(narrow_plain_lazy(Lp, R1, sx, cl, ch, m, sh), inc2, t2);
+                bad += (inc2 != inc) || (t2 != t) || (Lp != st.Lp) || ((R1 >> sx) != new_range) || (sx && (R1 & 1u)) ||
+                       R1 <= 32768u || R1 > 65536u;
+            }
+        }
+        for (uint32_t products = 0; products < 2u; ++products) {   // decoders
+            DecState st{(code0 - lo16) & 0xFFFFu, lo16, range};
+            BitSource in;
+            in.start(window, 64u);
+            if (products) narrow_track_products(st, cl * range, ch * range, m, sh, in);
+            else narrow_track(st, cl, ch, m, sh, in);
+            const uint64_t left = taken ? window << taken : window;
+            bad += (st.D != (((uint32_t)code - Lr) & 0xFFFFu)) || (st.L != Lr) || (st.R != new_range) ||
+                   (in.have != 64u - taken) || (in.hi != (uint32_t)(left >> 32)) || (in.lo != (uint32_t)left);
         }
     }
     return bad;

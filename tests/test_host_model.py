@@ -1,4 +1,4 @@
-"""Closed forms used by the CUDA kernels (gpuar_b200/csrc/coder_math.h), compiled for the
+"""Closed forms used by the CUDA kernels (gpuar_b200/csrc/coder_math.h, encode_math.h, decode_math.h), compiled for the
 host and driven through a lane-by-lane emulation of the kernels' data flow
 (tests/host_model.cpp), against the oracle and the reference's golden vectors.  CPU only."""
 import ctypes as C
@@ -26,19 +26,11 @@ def model():
     lib = C.CDLL(SO)
     lib.host_model_encode_stream.restype = C.c_size_t
     lib.host_model_encode_stream.argtypes = [O._u8p, C.c_size_t, O._u8p, C.c_uint32]
-    lib.host_model_encode_stream_plain.restype = C.c_size_t
-    lib.host_model_encode_stream_plain.argtypes = [O._u8p, C.c_size_t, O._u8p, C.c_uint32]
-    lib.host_model_carry_events.restype = C.c_uint64
     lib.host_model_encode_stream_ws.restype = C.c_size_t
     lib.host_model_encode_stream_ws.argtypes = [O._u8p, C.c_size_t, O._u8p, C.c_uint32]
+    lib.host_model_carry_events.restype = C.c_uint64
     lib.host_model_decode_packet.restype = C.c_uint32
-    lib.host_model_decode_packet.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p]
-    lib.host_model_decode_packet_early.restype = C.c_uint32
-    lib.host_model_decode_packet_early.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p]
-    lib.host_model_decode_packet_total.restype = C.c_uint32
-    lib.host_model_decode_packet_total.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p, C.c_int]
-    lib.host_model_decode_packet_v2.restype = C.c_uint32
-    lib.host_model_decode_packet_v2.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p, C.c_int]
+    lib.host_model_decode_packet.argtypes = [O._u8p, C.c_size_t, C.c_size_t, O._u8p, C.c_int]
     lib.host_model_check_division.restype = C.c_uint64
     lib.host_model_check_division.argtypes = [C.c_uint32, C.c_uint32]
     lib.host_model_check_renorm.restype = C.c_uint64
@@ -48,31 +40,29 @@ def model():
     return lib
 
 
-def model_encode(lib, data, packet=8192, ws=False, plain=False):
+def model_encode(lib, data, packet=8192, ws=False):
+    """encode_kernel's lane (ws=False) or the stages of encode_ws_kernel (ws=True)"""
     buf = np.zeros(O.n_packets(data.size, packet) * (packet + 512) + 64, np.uint8)
     src = data if data.size else np.zeros(1, np.uint8)
     fn = lib.host_model_encode_stream_ws if ws else lib.host_model_encode_stream
-    if plain:                              # encode_math.h: plain window, carry into the pending bits
-        fn = lib.host_model_encode_stream_plain
     return buf[: fn(O._ptr(src), data.size, O._ptr(buf), packet)].copy()
 
 
-def model_decode(lib, pay, n, early=False, total=False, v2=None):
-    fn = lib.host_model_decode_packet_early if early else lib.host_model_decode_packet
-    if v2 is not None:                     # decode_math.h: 0 = throughput step, 1 = latency step
-        def fn(p, r, o, out):
-            return lib.host_model_decode_packet_v2(p, r, o, out, v2)
-    if total:
-        def fn(p, r, o, out, _early=int(early)):
-            return lib.host_model_decode_packet_total(p, r, o, out, _early)
+def model_decode(lib, pay, n, latency=False):
+    """decode_kernel's lane: the throughput step or the latency step (decode_math.h)"""
     c = pay.size
     padded = np.zeros((c + 64 + 15) // 16 * 16, np.uint8)
     padded[:c] = pay
     out = np.zeros(n + O.PACKET, np.uint8)
     pos = 0
     for o in O.index(pay):
-        pos += fn(O._ptr(padded), c + 64, int(o), out[pos:].ctypes.data_as(O._u8p))
+        pos += lib.host_model_decode_packet(O._ptr(padded), c + 64, int(o), out[pos:].ctypes.data_as(O._u8p), int(latency))
     return out[:pos]
+
+
+def both_decoders_return(lib, pay, data):
+    for latency in (False, True):
+        assert np.array_equal(model_decode(lib, pay, data.size, latency), data)
 
 
 def test_reciprocal_division_is_exact(model):
@@ -100,13 +90,7 @@ def test_kernel_math_matches_reference_golden(model, name):
     pay = model_encode(model, data)
     assert pay.size == rec["payload_bytes"] and md5(pay) == rec["payload_md5"]
     assert np.array_equal(model_encode(model, data, ws=True), pay)
-    assert np.array_equal(model_encode(model, data, plain=True), pay)
-    assert np.array_equal(model_decode(model, pay, data.size), data)
-    assert np.array_equal(model_decode(model, pay, data.size, early=True), data)
-    assert np.array_equal(model_decode(model, pay, data.size, early=True, total=True), data)
-    assert np.array_equal(model_decode(model, pay, data.size, total=True), data)
-    for v in range(2):
-        assert np.array_equal(model_decode(model, pay, data.size, v2=v), data)
+    both_decoders_return(model, pay, data)
 
 
 @pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 63, 64, 65, 4095, 8191, 8192])
@@ -115,13 +99,7 @@ def test_kernel_math_ragged_lengths(model, n):
         pay = model_encode(model, data)
         assert np.array_equal(pay, O.encode(data))
         assert np.array_equal(model_encode(model, data, ws=True), pay)
-        assert np.array_equal(model_encode(model, data, plain=True), pay)
-        assert np.array_equal(model_decode(model, pay, n), data)
-        assert np.array_equal(model_decode(model, pay, n, early=True), data)
-        assert np.array_equal(model_decode(model, pay, n, early=True, total=True), data)
-        assert np.array_equal(model_decode(model, pay, n, total=True), data)
-        for v in range(2):
-            assert np.array_equal(model_decode(model, pay, n, v2=v), data)
+        both_decoders_return(model, pay, data)
 
 
 @pytest.mark.parametrize("packet", [4096, 12288, 16112])
@@ -132,30 +110,21 @@ def test_kernel_math_other_packet_sizes(model, packet):
     pay = model_encode(model, data, packet)
     assert pay.size == rec["payload_bytes"] and md5(pay) == rec["payload_md5"]
     assert np.array_equal(model_encode(model, data, packet, ws=True), pay)
-    assert np.array_equal(model_encode(model, data, packet, plain=True), pay)
-    assert np.array_equal(model_decode(model, pay, data.size), data)
-    assert np.array_equal(model_decode(model, pay, data.size, early=True), data)
-    assert np.array_equal(model_decode(model, pay, data.size, early=True, total=True), data)
-    assert np.array_equal(model_decode(model, pay, data.size, total=True), data)
-    for v in range(2):
-        assert np.array_equal(model_decode(model, pay, data.size, v2=v), data)
+    both_decoders_return(model, pay, data)
 
 
 def test_kernel_math_long_underflow_runs(model):
-    # two-symbol inputs straddling the midpoint keep the coder in the 01../10.. state
+    # two-symbol inputs straddling the midpoint keep the coder in the 01../10.. state; the greedy straddle
+    # packet drives the reference's pending-underflow counter into the thousands
     rng = np.random.default_rng(5)
     carries_before = model.host_model_carry_events()
-    straddle, max_pend = D.straddle_packet(8192, report=True)     # pending-underflow counter in the thousands
+    straddle, max_pend = D.straddle_packet(8192, report=True)
     assert max_pend > 1000
     for k in range(9):
         data = straddle if k == 8 else rng.choice(np.array([127, 128], np.uint8), size=8192, p=[0.5, 0.5])
         pay = model_encode(model, data)
         assert np.array_equal(pay, O.encode(data))
         assert np.array_equal(model_encode(model, data, ws=True), pay)
-        assert np.array_equal(model_encode(model, data, plain=True), pay)
-        assert np.array_equal(model_decode(model, pay, 8192), data)
-        assert np.array_equal(model_decode(model, pay, 8192, early=True, total=True), data)
-        for v in range(2):
-            assert np.array_equal(model_decode(model, pay, 8192, v2=v), data)
-    # the plain-window encoder had to carry into words it had already stored (its rare path) on these inputs
+        both_decoders_return(model, pay, data)
+    # the encoder had to carry into words it had already stored (the kernels' rare path) on these inputs
     assert model.host_model_carry_events() > carries_before
