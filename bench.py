@@ -79,7 +79,8 @@ def kernel_source_hash():
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "gpuar_b200", "csrc")
-    for name in ("coder_math.h", "common.cuh", "lookback.cuh", "shard.cuh", "encode.cu", "encode_ws.cu", "decode.cu"):
+    for name in ("coder_math.h", "encode_math.h", "decode_math.h", "common.cuh", "lookback.cuh", "shard.cuh", "encode.cu",
+                 "encode_ws.cu", "decode.cu"):
         h.update(open(os.path.join(d, name), "rb").read())
     return h.hexdigest()[:16]
 
