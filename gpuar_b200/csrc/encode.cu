@@ -29,7 +29,13 @@
 #include "lookback.cuh"
 #include "shard.cuh"
 
+#ifndef GPUAR_ENC_Q_UNROLL
+#define GPUAR_ENC_Q_UNROLL 1        // tuning knob: input words (4 symbols each) per pass of the steady-state loop
+#endif
+
 namespace gpuar {
+
+constexpr int kEncWordsPerPass = GPUAR_ENC_Q_UNROLL;
 
 // ------------------------------------------------------------------ encode
 struct EncShared {
@@ -103,7 +109,7 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
 
     // 16 symbols held in `c`; `nx` = the word that follows them (first word of the next chunk)
     auto half = [&](const uint4 &c, uint32_t nx, bool fast, uint32_t i0, uint32_t h, uint32_t m_l, uint32_t sh) {
-#pragma unroll 1
+#pragma unroll kEncWordsPerPass
         for (uint32_t q = 0; q < 4u; ++q) {
             // 4 symbols per inner iteration keeps the loop body inside the instruction cache
             const uint32_t word = q == 0u ? c.x : q == 1u ? c.y : q == 2u ? c.z : c.w;
