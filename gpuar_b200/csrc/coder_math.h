@@ -58,11 +58,15 @@ GPUAR_HD uint32_t bswap32(uint32_t x)
 // i.e. at i = 256, 768, 1792, 3840, 7936 -- all multiples of 32, so it is constant over
 // any aligned run of 32 positions.
 GPUAR_HD uint32_t shift_for(uint32_t T) { return 30u - clz32(T); }
+// m in 32-bit arithmetic (a 64-bit division is a subroutine call on the device -- once per 32 steps in every
+// kernel, and it waited for the warp's outstanding loads): with A = 2^(16+sh) = q1 * T + r1,
+// 2^(32+sh) = A * 2^16, so m = q1 * 2^16 + ceil(r1 * 2^16 / T); r1 < T < 2^15 keeps everything below 2^32.
 GPUAR_HD uint32_t magic_for(uint32_t T, uint32_t &sh)
 {
     sh = shift_for(T);
-    const uint64_t two_p = 1ull << (32u + sh);
-    return (uint32_t)((two_p + T - 1u) / T);
+    const uint32_t A = 1u << (16u + sh);
+    const uint32_t q1 = A / T, r1 = A - q1 * T;
+    return (q1 << 16) + ((r1 << 16) + T - 1u) / T;
 }
 GPUAR_HD uint32_t div_total(uint32_t n, uint32_t m, uint32_t sh) { return mulhi32(n, m) >> sh; }
 

@@ -139,10 +139,16 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
         sh = shift_for(256u + i0);                                // the shift is uniform over the round
         // fast rounds: not the first (nothing pending yet at i = 0), and position i0+32 exists in every lane
         const bool fast = r != 0u && i0 + 33u <= min_len;
+        // The next chunk of a buffer is requested at the START of the half round that still reads the buffer, into
+        // other registers, and moved over at its end: every register read then waits for a load issued 16 steps
+        // earlier.  (Requested at the end of the half round, the load shared its scoreboard with the other buffer's,
+        // whose first read came right behind it: ncu showed 9 % of the warp time waiting there.)
+        const uint4 nextA = fetch(2u * r + 2u);
         half(bufA, bufB.x, fast, i0, 0u, m_l, sh);
-        bufA = fetch(2u * r + 2u);                                // consumed 12+ steps from now
+        bufA = nextA;
+        const uint4 nextB = fetch(2u * r + 3u);
         half(bufB, bufA.x, fast, i0, 1u, m_l, sh);
-        bufB = fetch(2u * r + 3u);
+        bufB = nextB;
     }
     if (pending) bits(std::false_type{});                         // BITS of the last step
 
