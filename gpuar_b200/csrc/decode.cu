@@ -41,15 +41,17 @@ __device__ __forceinline__ const uint32_t *clamp_ptr(const uint32_t *p, const ui
     return p < last ? p : last;          // reads past the buffer are pinned to its last word
 }
 
-constexpr uint32_t kRing = 8;        // per-lane ring of stream words in shared memory
+constexpr uint32_t kRing = 8;        // per-lane ring of stream words in shared memory (latency variant)
+constexpr uint32_t kRingSmall = 4;   // ... of the throughput variant: 512 B is what 10 CTAs per SM leave free
 constexpr uint32_t kAhead = 3;       // words requested ahead of the reader
 
 // kernel variants (template parameter kLatency): throughput (decode_step) and latency (decode_step_latency)
 template <bool kLatency>
 struct DecShared;
 template <>
-struct DecShared<false> {                    // throughput variant: 21504 B keeps 10 CTAs per SM
+struct DecShared<false> {                    // throughput variant: 22016 B keeps 10 CTAs per SM
     uint64_t tree[kTreeStored][32];          // lane l owns column l (banks 2l, 2l+1); root in registers
+    uint32_t ring[kRingSmall][32];           // 512 B stream ring
 };
 template <>
 struct DecShared<true> {                     // latency variant (at most 4 CTAs per SM: size does not matter)
@@ -70,19 +72,19 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
-// kRingFeed selects how the bit window is refilled:
-//   true   cp.async ring + predicated feed: nothing in the step ever waits on a global load and
-//          there is no divergent branch -- shortest dependent chain; used while every warp has a
-//          scheduler to itself (up to 4 warps per SM = 148 MiB: latency is everything);
-//   false  one word prefetched in a register, fed under a (divergent) branch -- fewer
-//          instructions per step; used when many warps per scheduler hide the latency.
-template <bool kRingFeed>
+// The bit window of both variants is refilled from a per-lane ring of stream words in shared memory that cp.async
+// (LDGSTS: no register, no scoreboard) keeps kAhead words ahead of the reader: nothing in a step ever waits on a
+// global load and the refill is predicated, never divergent.  (Round 1 fed the throughput variant from one word
+// prefetched in a register: the compiler had sunk that load to within a step of its use and 6 % of the warp time
+// waited for it; a 512-byte ring is what 10 CTAs per SM leave free: 4 GiB decode 27.1 -> 26.5 ms.)
+template <bool kLatency>
 __global__ void __launch_bounds__(32)
 decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64_t *__restrict__ offsets,
               uint32_t stride, uint32_t n_packets, uint8_t *__restrict__ out, uint32_t packet,
               const uint64_t *__restrict__ count)
 {
-    __shared__ __align__(16) DecShared<kRingFeed> sm;
+    __shared__ __align__(16) DecShared<kLatency> sm;
+    constexpr uint32_t kRingWords = kLatency ? kRing : kRingSmall;
     const uint32_t lane = lane_id();
     const uint32_t my = blockIdx.x * 32u + lane;
     if (count) {                                    // sharded decode: the chain discovery left the count on the device
@@ -96,7 +98,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     TopLevels top;                               // latency variants: the root's thresholds, level-1 copy
     uint64_t *tree = nullptr;
     LatTree lat{nullptr, nullptr, nullptr, 32u};
-    if constexpr (kRingFeed) {
+    if constexpr (kLatency) {
         lat = LatTree{&sm.l1[0][lane], &sm.l2[0][lane], &sm.l3[0][lane], 32u};
         lat_tree_init(top, lat);
     } else {
@@ -107,9 +109,8 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     // bit source: aligned 32-bit words of the packet's bitstream.  The window is fed from a
     // per-lane ring in shared memory that cp.async keeps kAhead words ahead of the reader.
     const uint32_t *const wend = reinterpret_cast<const uint32_t *>(payload) + (readable >> 2) - 1;  // last readable word
-    const uint32_t *gp = wend;      // next word to request (ring) / word held in `ahead` (register)
-    uint32_t rd = 0;                // ring feed: words consumed
-    uint32_t ahead = 0;             // register feed: prefetched word, byte-swapped only when fed
+    const uint32_t *gp = wend;      // next word to request
+    uint32_t rd = 0;                // words consumed from the ring
     BitSource in;
     in.start(0, 64u);
     uint32_t raw = 0;
@@ -131,38 +132,27 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
     // and 32-bit index arithmetic do (a 64-bit pointer to bump and clamp costs four instructions more)
     const uint32_t *const g0 = clamp_ptr(gp, wend);
     const uint32_t p_max = (uint32_t)min((ptrdiff_t)(wend - g0), (ptrdiff_t)0x3FFFFFFF);
-    uint32_t ring_s = 0;
-    if constexpr (kRingFeed) ring_s = (uint32_t)__cvta_generic_to_shared(&sm.ring[0][lane]);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(&sm.ring[0][lane]);
     auto request = [&](uint32_t p) {
-        const uint32_t dst = ring_s + ((p & (kRing - 1u)) << 7);
+        const uint32_t dst = ring_s + ((p & (kRingWords - 1u)) << 7);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(g0 + min(p, p_max)) : "memory");
     };
-    if (kRingFeed) {
-        for (uint32_t p = 0; p < kAhead; ++p) request(p);
-        cp_async_commit();
-        cp_async_wait<0>();
-    } else {
-        ahead = *clamp_ptr(gp, wend);
-    }
+    for (uint32_t p = 0; p < kAhead; ++p) request(p);
+    cp_async_commit();
+    cp_async_wait<0>();
     auto refill = [&]() {
-        if (kRingFeed) {
-            // One refill per two steps (below), predicated, never divergent: feed the ring's next word if the
-            // window has room, and request one more word.  A word is read at least kAhead steps
-            // after it was requested, so waiting for all but the kAhead-1 newest groups makes it
-            // visible.
-            cp_async_wait<kAhead - 1>();
-            uint32_t w;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(ring_s + ((rd & (kRing - 1u)) << 7)) : "memory");
-            const bool h = in.hungry();
-            in.feed_if(h, bswap32(w));
-            if (h) request(rd + kAhead);
-            cp_async_commit();
-            rd += h ? 1u : 0u;
-        } else if (in.hungry()) {
-            in.feed(bswap32(ahead));
-            ++gp;
-            ahead = *clamp_ptr(gp, wend);
-        }
+        // One refill per two steps (below), predicated, never divergent: feed the ring's next word if the
+        // window has room, and request one more word.  A word is read at least kAhead refills
+        // after it was requested, so waiting for all but the kAhead-1 newest groups makes it
+        // visible.
+        cp_async_wait<kAhead - 1>();
+        uint32_t w;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(ring_s + ((rd & (kRingWords - 1u)) << 7)) : "memory");
+        const bool h = in.hungry();
+        in.feed_if(h, bswap32(w));
+        if (h) request(rd + kAhead);
+        cp_async_commit();
+        rd += h ? 1u : 0u;
     };
     // initializeDecoder (:582-603): the first 16 bits; lower bound 0, range 2^16
     DecState st;
@@ -181,7 +171,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
         // latency variant: every level decided by multiplication, speculative node loads; throughput variant: the
         // quotient first, then the plain tree (the other way round was measured on both, profiles/r2_decode_v2.md)
         uint32_t s;
-        if constexpr (kRingFeed) s = decode_step_latency(st, top, lat, T, m, sh, in);
+        if constexpr (kLatency) s = decode_step_latency(st, top, lat, T, m, sh, in);
         else s = decode_step(st, root, tree, 32u, T, m, sh, in);
         packed = mad32(s, 1u << (8u * slot), packed);               // fields cannot overlap: a multiply-add, not shift + or
         // A step takes at most 16 bits and the window holds at least 33 after a refill: one refill (at most one
@@ -198,7 +188,7 @@ decode_kernel(const uint8_t *__restrict__ payload, size_t readable, const uint64
         sh = shift_for(256u + i0);                                 // the shift is uniform over the round
         if (i0 + 32u <= min_raw) {
             // every lane of the warp has all 32 positions: no per-lane predicates
-            constexpr int kUnroll = kRingFeed ? kDecUnrollLat : kDecUnroll;
+            constexpr int kUnroll = kLatency ? kDecUnrollLat : kDecUnroll;
 #pragma unroll kUnroll
             for (uint32_t j = 0; j < 32u; ++j) {
                 step(i0 + j, __shfl_sync(kFull, m_l, j), sh, j & 3u);
