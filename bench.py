@@ -75,13 +75,18 @@ PREFIX_GOLDEN = {("mixed", 3): "m1m", ("and3", 2): "s1m", ("uniform", 0x64): "u6
 
 
 def kernel_source_hash():
-    """sha256 over the kernel sources: ties profiles/traffic.json (ncu DRAM bytes) to the code it was captured from."""
+    """sha256 over the kernel sources with comments and blank space removed: ties profiles/traffic.json (ncu DRAM
+    bytes) to the code it was captured from, not to its commentary."""
     import hashlib
+    import re
     h = hashlib.sha256()
     d = os.path.join(ROOT, "gpuar_b200", "csrc")
     for name in ("coder_math.h", "encode_math.h", "decode_math.h", "common.cuh", "lookback.cuh", "shard.cuh", "encode.cu",
                  "encode_ws.cu", "decode.cu"):
-        h.update(open(os.path.join(d, name), "rb").read())
+        text = open(os.path.join(d, name), encoding="utf-8").read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)            # block comments
+        text = re.sub(r"//[^\n]*", "", text)                         # line comments (no string of these files holds //)
+        h.update(re.sub(r"\s+", " ", text).encode())
     return h.hexdigest()[:16]
 
 

@@ -31,7 +31,7 @@
 namespace gpuar {
 
 #ifndef GPUAR_DEC_UNROLL_LAT
-#define GPUAR_DEC_UNROLL_LAT 8      // the same for the latency variants (a lone warp: 64 MiB decode 1.382 ms with 4, 1.350 with 8)
+#define GPUAR_DEC_UNROLL_LAT 8      // the same for the latency variant (a lone warp: 64 MiB decode 1.382 ms with 4, 1.350 with 8; 16 overflows the instruction cache)
 #endif
 constexpr int kDecUnroll = GPUAR_DEC_UNROLL;
 constexpr int kDecUnrollLat = GPUAR_DEC_UNROLL_LAT;
@@ -54,7 +54,7 @@ struct DecShared<false> {                    // throughput variant: 22016 B keep
     uint32_t ring[kRingSmall][32];           // 512 B stream ring
 };
 template <>
-struct DecShared<true> {                     // latency variant (at most 4 CTAs per SM: size does not matter)
+struct DecShared<true> {                     // latency variant: 23.5 KB, used up to 8 CTAs per SM (9 would fit)
     Quad l1[4][32];                          // level-1 thresholds as 32-bit words (16 B per lane and node)
     uint64_t l2[16][32];                     // packed (0, t0, t1, t2)
     uint64_t l3[64][32];                     // leaves: packed inclusive sums

@@ -13,10 +13,12 @@
 //          memory (coder_math.h: tree_encode): root in registers, three independent 8-byte
 //          loads/stores, byte permutes instead of branches.  Equals the reference's two
 //          Fenwick prefix sums + update (gpuar_kernel.cu:215-238).
-//   CODER  the interval recurrence (gpuar_kernel.cu:256-288) and the renormalisation
-//          loop (:321-367) in closed form.
-//   BITS   the step's output field appended to a 64-bit accumulator, flushed as 32-bit
-//          words into the packet's slot.
+//   CODER  the interval recurrence (gpuar_kernel.cu:256-288) with the renormalisation loop
+//          (:321-367) as a single normalisation on the plain window of the lower bound
+//          (encode_math.h: narrow_plain).
+//   BITS   the bits that left the window, plus the carry, added into a 64-bit accumulator
+//          (the stream is the lower bound written out as one long number: no pending-underflow
+//          counter), flushed as 32-bit words into the packet's slot (CarrySink).
 // Only CODER is a loop-carried dependent chain.  The three stages are software pipelined
 // inside each lane -- iteration i runs BITS(i-1), CODER(i), MODEL(i+1), which are mutually
 // independent -- so the chain of one step overlaps the model and bit-packing work of its
@@ -66,7 +68,7 @@ encode_kernel(const uint8_t *__restrict__ src, size_t n, uint8_t *__restrict__ s
     CarrySink out;
     out.start(reinterpret_cast<uint32_t *>(slot + kHdr), mine ? ((slot_stride - kHdr) >> 2) : 0u);
 
-    // 16 input bytes per lane per half round, fetched one half round ahead.  The read may
+    // 16 input bytes per lane per half round, requested a whole round before their first use.  The read may
     // run up to 15 bytes past n inside the caller's 16-byte-rounded buffer (API contract).
     const uint4 *const in16 = reinterpret_cast<const uint4 *>(src + off);
     auto fetch = [&](uint32_t g) -> uint4 {
