@@ -238,6 +238,41 @@ def test_both_decode_kernels_are_bit_exact(dev, path):
         _lib.set_option(_lib.OPT_DECODE_PATH, 0)
 
 
+def test_random_distributions_all_kernels(dev):
+    # one stream of packets with heavy skew, runs, ramps, two-symbol alphabets and sorted bytes (the fixed vectors
+    # hold none of these) through every encode path and both decode kernels, against the oracle
+    from gpuar_b200 import _lib
+    rng = np.random.default_rng(20261017)
+    parts = []
+    for k in range(66):
+        n = 8192
+        kind = k % 6
+        if kind == 0:
+            parts.append(rng.choice(256, size=n, p=rng.dirichlet(np.full(256, 0.02))).astype(np.uint8))
+        elif kind == 1:
+            parts.append(np.repeat(rng.integers(0, 256, size=n // 37 + 1, dtype=np.uint8), 37)[:n])
+        elif kind == 2:
+            parts.append((np.arange(n) // int(rng.integers(1, 65))).astype(np.uint8))
+        elif kind == 3:
+            parts.append(rng.choice(np.array([0, 255], np.uint8), size=n, p=[0.97, 0.03]))
+        elif kind == 4:
+            parts.append(np.minimum(rng.geometric(0.3, size=n) - 1, 255).astype(np.uint8))
+        else:
+            parts.append(np.sort(rng.integers(0, 256, size=n, dtype=np.uint8)))
+    data = np.concatenate(parts + [parts[0][:777]])
+    want = O.encode(data)
+    try:
+        for enc in (0, 1, 2):
+            _lib.set_option(_lib.OPT_ENCODE_PATH, enc)
+            assert np.array_equal(dev_encode(dev, data), want), enc
+        for dec in (1, 2):
+            _lib.set_option(_lib.OPT_DECODE_PATH, dec)
+            assert np.array_equal(dev.decode_bytes(to_dev(want)).cpu().numpy(), data), dec
+    finally:
+        _lib.set_option(_lib.OPT_ENCODE_PATH, 0)
+        _lib.set_option(_lib.OPT_DECODE_PATH, 0)
+
+
 def test_device_selfcheck_of_the_quotient():
     # divide_floor (one-sided float estimate) over every range and quotient, on the device
     from gpuar_b200 import _lib

@@ -128,3 +128,30 @@ def test_kernel_math_long_underflow_runs(model):
         both_decoders_return(model, pay, data)
     # the encoder had to carry into words it had already stored (the kernels' rare path) on these inputs
     assert model.host_model_carry_events() > carries_before
+
+
+def test_kernel_math_random_distributions(model):
+    # seeded sweep over byte distributions the fixed vectors do not hold: heavy skew (a few symbols take almost all
+    # the mass, so counts run high and intervals get narrow), runs, ramps, two-symbol alphabets at both ends of the
+    # byte range, random lengths around the packet size
+    rng = np.random.default_rng(20261017)
+    for k in range(48):
+        n = int(rng.integers(1, 3 * 8192 + 1))
+        kind = k % 6
+        if kind == 0:
+            p = rng.dirichlet(np.full(256, 0.02))
+            data = rng.choice(256, size=n, p=p).astype(np.uint8)
+        elif kind == 1:
+            data = np.repeat(rng.integers(0, 256, size=n // 37 + 1, dtype=np.uint8), 37)[:n]
+        elif kind == 2:
+            data = (np.arange(n) // int(rng.integers(1, 65))).astype(np.uint8)
+        elif kind == 3:
+            data = rng.choice(np.array([0, 255], np.uint8), size=n, p=[0.97, 0.03])
+        elif kind == 4:
+            data = np.minimum(rng.geometric(0.3, size=n) - 1, 255).astype(np.uint8)
+        else:
+            data = np.sort(rng.integers(0, 256, size=n, dtype=np.uint8))
+        pay = model_encode(model, data)
+        assert np.array_equal(pay, O.encode(data)), (k, n)
+        assert np.array_equal(model_encode(model, data, ws=True), pay), (k, n)
+        both_decoders_return(model, pay, data)
