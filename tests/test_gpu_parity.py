@@ -78,9 +78,14 @@ def straddle_stream():
     st = D.straddle_packet(8192)
     parts = []
     for p in range(70):
-        parts.append(st if p % 3 == 0 else st[: 8192 - 7 * p][::1] if p % 7 == 3 else
-                     rng.choice(np.array([127, 128], np.uint8), size=8192) if p % 3 == 1 else D.uniform(p, 8192))
-    parts = [np.resize(a, 8192) for a in parts]
+        if p % 3 == 0:
+            parts.append(st)
+        elif p % 7 == 3:
+            parts.append(np.resize(st[: 8192 - 7 * p], 8192))      # the straddle run restarts inside the packet
+        elif p % 3 == 1:
+            parts.append(rng.choice(np.array([127, 128], np.uint8), size=8192))
+        else:
+            parts.append(D.uniform(p, 8192))
     return np.concatenate(parts + [st[:4097]])
 
 
